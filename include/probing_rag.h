@@ -1,0 +1,143 @@
+/* probing_rag.h -- C ABI of libprobingrag.so, the B200 (sm_100a) retrieval hot path of
+ * Probing-RAG: batched BM25 scoring + top-k over a CSR inverted index in HBM, the k-way
+ * merge of per-shard candidate lists, and the prober gate.
+ *
+ * The reference (baekingeol/Probing-RAG) is pure Python and has no FFI; each entry point
+ * below names the reference call it replaces.  Host code stays Python/PyTorch and binds
+ * these symbols with ctypes; no torch types cross this boundary.
+ *
+ * Conventions
+ *   - every function returns PR_OK (0) or a negative PR_E* code; pr_last_error() gives the
+ *     thread-local message of the last failure on the calling thread.
+ *   - all *_dev pointers are device pointers on the handle's device, owned by the caller
+ *     (PyTorch tensors); the library allocates no device memory.
+ *   - work is enqueued on the caller's stream; results are valid once that stream is
+ *     synchronised.  No entry point synchronises the host except where stated.
+ *   - ranked lists use the canonical total order: score descending, doc id ascending.
+ *     Missing entries (fewer candidates than k) are (-INFINITY, -1).
+ */
+#ifndef PROBING_RAG_H
+#define PROBING_RAG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PR_VERSION 100 /* 0.1.0 */
+
+#define PR_OK 0
+#define PR_EINVAL (-1)     /* bad argument (null pointer, k out of range, misaligned buffer) */
+#define PR_ECUDA (-2)      /* a CUDA runtime call failed; message in pr_last_error()         */
+#define PR_ERANGE (-3)     /* k > number of documents, or a term id outside [0, n_terms)     */
+#define PR_EWORKSPACE (-4) /* workspace_bytes smaller than pr_bm25_workspace_bytes()         */
+#define PR_EUNSUPPORTED (-5)
+
+#define PR_MAX_K 128
+
+typedef struct pr_index pr_index_t;
+typedef void *pr_stream_t; /* cudaStream_t */
+
+/* Tunables of the BM25 scoring kernel; zero fields keep the default. */
+typedef struct pr_bm25_tuning {
+    int32_t tile_docs;      /* documents per shared-memory score tile (multiple of 4*threads) */
+    int32_t tiles_per_item; /* consecutive tiles one CTA scores for one query                 */
+    int32_t threads;        /* 256, 512 or 1024                                               */
+    int32_t mode;           /* 1 = full-tile scan select; 2 = threshold-on-update select      */
+    int32_t min_items;      /* doc ranges are split until a launch has this many work items   */
+    int32_t cand_cap;       /* candidate buffer entries per CTA (mode 2)                      */
+} pr_bm25_tuning_t;
+
+int pr_version(void);
+const char *pr_last_error(void);
+
+/* Inverted index handle over caller-owned device arrays -- the {data, indices, indptr,
+ * num_docs} that bm25s.BM25.index() builds inside BM25Retriever.from_defaults
+ * (/root/reference/exp_rag.py:242), term-major with ascending doc ids:
+ *   indptr_dev  int64[n_terms+1], doc_ids_dev int32[nnz] (LOCAL ids, 0-based, ascending per
+ *   term), weights_dev float[nnz] (>= 0; precomputed idf*tfc).  doc_ids_dev and weights_dev
+ *   must be 16-byte aligned.  n_docs is this shard's document count, doc_id_base the global
+ *   id of local doc 0, n_docs_global the whole corpus size (k is checked against it).
+ * Validates the arrays on the device and synchronises once. */
+int pr_index_create(pr_index_t **out, int device, int64_t n_docs_global, int32_t doc_id_base,
+                    int32_t n_docs, int32_t n_terms, int64_t nnz, const int64_t *indptr_dev,
+                    const int32_t *doc_ids_dev, const float *weights_dev);
+int pr_index_destroy(pr_index_t *index);
+int pr_index_set_tuning(pr_index_t *index, const pr_bm25_tuning_t *tuning);
+int pr_index_get_tuning(const pr_index_t *index, pr_bm25_tuning_t *tuning);
+
+/* Bytes of scratch pr_bm25_topk needs for a batch of n_queries at depth k. */
+size_t pr_bm25_workspace_bytes(const pr_index_t *index, int32_t n_queries, int32_t k);
+
+/* Batched BM25Retriever.retrieve (/root/reference/exp_rag.py:426, 428, 492; utils.py:640;
+ * bm25s.BM25.retrieve + selection.topk) at token-id level.
+ *   q_indptr_dev int64[n_queries+1], q_terms_dev int32[nnzq]: CSR batch of query term ids in
+ *   query-token order, duplicates kept.  Scores are accumulated in fp32 in that order, one
+ *   rounded add per posting, exactly as the reference's dense accumulator does.
+ *   out_scores_dev float[n_queries*k], out_doc_ids_dev int32[n_queries*k] (GLOBAL doc ids).
+ * Fewer than k positive scores: the tail is filled with this shard's lowest doc ids at
+ * score 0.0.  A term id outside [0, n_terms) is skipped and flagged: pr_bm25_status() reports
+ * PR_ERANGE after the stream is synchronised. */
+int pr_bm25_topk(pr_index_t *index, int32_t n_queries, const int64_t *q_indptr_dev,
+                 const int32_t *q_terms_dev, int32_t k, float *out_scores_dev,
+                 int32_t *out_doc_ids_dev, void *workspace_dev, size_t workspace_bytes,
+                 pr_stream_t stream);
+
+/* Reads the status word pr_bm25_topk left in the workspace (synchronises `stream`). */
+int pr_bm25_status(const void *workspace_dev, pr_stream_t stream);
+
+/* Per-kernel timing for bench.py's roofline line: when enabled, pr_bm25_topk brackets every
+ * launch of the scoring kernel with CUDA events on the caller's stream; pr_bm25_profile waits
+ * for them and returns the summed device time and the launch count of the last call. */
+int pr_index_set_profiling(pr_index_t *index, int enable);
+int pr_bm25_profile(pr_index_t *index, float *score_ms, int32_t *score_launches);
+
+/* Kernel launches the last pr_bm25_topk call on this handle enqueued (for bench accounting). */
+int64_t pr_bm25_last_launches(const pr_index_t *index);
+
+/* k-way merge of per-shard ranked lists (the step after the NCCL all-gather):
+ *   scores_dev float[n_lists, n_queries, k], ids_dev int32[n_lists, n_queries, k]
+ *   -> out_scores_dev float[n_queries, k], out_ids_dev int32[n_queries, k].
+ * Entries with id < 0 are ignored. */
+int pr_topk_merge(int32_t n_queries, int32_t k, int32_t n_lists, const float *scores_dev,
+                  const int32_t *ids_dev, float *out_scores_dev, int32_t *out_ids_dev,
+                  pr_stream_t stream);
+
+/* ---- prober gate ------------------------------------------------------------------------
+ * Six ImprovedProbe MLPs (/root/reference/utils.py:29-57) + softmax-sum gate
+ * (/root/reference/exp_rag.py:407-415) + stream compaction of the "retrieve" rows. */
+#define PR_PROBER_MAX 8
+
+typedef struct pr_prober_weights {
+    int32_t d_model;  /* 2048 */
+    int32_t hidden;   /* 512  */
+    /* fp32 vectors, caller-owned device memory (state_dict tensors as they are) */
+    const float *ln_in_w, *ln_in_b; /* [d_model] layer_norm_input.{weight,bias} */
+    const float *b1;                /* [hidden]  fc1.bias                        */
+    const float *ln1_w, *ln1_b;     /* [hidden]  layer_norm1                     */
+    const float *b2;                /* [hidden]  fc2.bias                        */
+    const float *ln2_w, *ln2_b;     /* [hidden]  layer_norm2                     */
+    const float *w3, *b3;           /* [2,hidden], [2]  fc3 (kept fp32)          */
+    /* bf16 matrices, row-major [out, in] like nn.Linear.weight, 128-byte aligned */
+    const void *w1_bf16;            /* [hidden, d_model] */
+    const void *w2_bf16;            /* [hidden, hidden]  */
+} pr_prober_weights_t;
+
+size_t pr_prober_workspace_bytes(int32_t n_probers, int32_t n_rows, int32_t d_model, int32_t hidden);
+
+/* X_dev float[n_rows, n_probers, d_model] (pooled hidden states, exp_rag.py:385-386).
+ * out_logits_dev float[n_rows, n_probers, 2] (may be NULL), out_probsum_dev float[n_rows, 2],
+ * out_retrieve_mask_dev uint8[n_rows] (1 = retrieve), out_compact_idx_dev int32[n_rows]
+ * (row indices with mask 1, ascending, first *out_n_retrieve_dev entries valid). */
+int pr_prober_forward(const pr_prober_weights_t *probers, int32_t n_probers, int32_t n_rows,
+                      const float *X_dev, float theta, int32_t ablation, float *out_logits_dev,
+                      float *out_probsum_dev, uint8_t *out_retrieve_mask_dev,
+                      int32_t *out_compact_idx_dev, int32_t *out_n_retrieve_dev,
+                      void *workspace_dev, size_t workspace_bytes, pr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROBING_RAG_H */

@@ -1,0 +1,839 @@
+// Batched BM25 scoring + top-k over a term-major CSR inverted index in HBM (sm_100a).
+//
+// Replaces, at token-id level, what BM25Retriever.retrieve does on the CPU for one query at a
+// time (/root/reference/exp_rag.py:426,428,492; utils.py:640 -> bm25s `_compute_relevance_
+// from_scores` + `selection.topk`): a dense fp32 accumulator over all
+// documents, one `scores[doc] += w` per posting of every query token in query order, then
+// top-k.  Here:
+//
+//   * the document range is cut into tiles of `tile_docs` fp32 accumulators that live in
+//     SHARED MEMORY; the dense N-float array of the reference never exists in HBM;
+//   * a work item is (query, chunk of `tiles_per_item` consecutive tiles); CTAs are persistent
+//     and pull items from an atomic counter;
+//   * inside a tile the query's terms are applied ONE TERM AT A TIME with a CTA barrier in
+//     between.  A document occurs at most once in a term's posting list, so the plain
+//     read-add-write into shared memory needs no atomics, and every document's score is
+//     summed in query-token order in fp32 -- bit-identical to the reference's accumulator;
+//   * postings are read with 128-bit streaming loads (4 doc ids + 4 weights per lane);
+//     the (term, tile) posting range comes from a warp-collective 32-ary search;
+//   * selection: mode 1 scans the tile (fused with re-zeroing it) into per-warp register
+//     top-k lists; mode 2 tests each updated accumulator against the query's running k-th
+//     score (scores only grow, weights are >= 0) and touches only the few candidates;
+//   * launches walk the document range in ascending order, so the part of the index a
+//     launch reads (tens of MB) stays L2-resident across the whole query batch; after each
+//     launch a merge kernel folds the per-item lists into the per-query running top-k.
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxPassTerms = 256;  // query terms planned per pass (shared-memory plan arrays)
+constexpr int kLightDf = 128;       // posting lists this short are scanned whole, no search
+
+struct ScoreArgs {
+    const int64_t *__restrict__ indptr;
+    const int32_t *__restrict__ doc_ids;
+    const float *__restrict__ weights;
+    const int64_t *__restrict__ q_indptr;
+    const int32_t *__restrict__ q_terms;
+    const float *__restrict__ run_theta;  // [B] k-th score of the running list, -1 if not full
+    float *part_s;                        // [B][C][K]
+    int32_t *part_d;
+    int32_t *counter;
+    int32_t *status;
+    int64_t nnz;
+    int32_t n_docs, n_terms, doc_id_base, n_queries, K;
+    int32_t tile_docs, tiles_per_item, chunk0, n_chunks_launch;
+    int32_t mode;      // 1 scan, 2 threshold-on-update
+    int32_t cand_cap;
+};
+
+__host__ __device__ inline size_t score_smem_bytes(int tile_docs, int cand_cap, int nw, int K)
+{
+    size_t b = (size_t)tile_docs * 4;          // tile
+    b += (size_t)cand_cap * 8;                 // cand_off, cand_s
+    b += (size_t)nw * K * 8;                   // wl_s, wl_d
+    b += (size_t)kMaxPassTerms * 16;           // seg_b, seg_e (int64)
+    b += (size_t)nw * 4 + 64;                  // wl_n + misc
+    return (b + 15) & ~(size_t)15;
+}
+
+template <int NT, int E, int MINB>
+__global__ void __launch_bounds__(NT, MINB) bm25_score_kernel(const ScoreArgs a)
+{
+    constexpr int NW = NT / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = a.tile_docs;
+    const int K = a.K;
+    float *tile = reinterpret_cast<float *>(smem_raw);
+    int64_t *seg_b = reinterpret_cast<int64_t *>(tile + T);
+    int64_t *seg_e = seg_b + kMaxPassTerms;
+    int32_t *cand_off = reinterpret_cast<int32_t *>(seg_e + kMaxPassTerms);
+    float *cand_s = reinterpret_cast<float *>(cand_off + a.cand_cap);
+    float *wl_s = cand_s + a.cand_cap;
+    int32_t *wl_d = reinterpret_cast<int32_t *>(wl_s + NW * K);
+    int32_t *wl_n = wl_d + NW * K;
+    int32_t *s_item = wl_n + NW;
+    int32_t *s_cand_n = s_item + 1;
+    float *s_thr = reinterpret_cast<float *>(s_cand_n + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float4 *tile4 = reinterpret_cast<float4 *>(tile);
+    const int nv = T >> 2;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int v = tid; v < nv; v += NT) tile4[v] = zero4;
+
+    const int C = a.n_chunks_launch;
+    const int64_t n_items = (int64_t)a.n_queries * C;
+    WarpTopK<E> item;  // warp 0 only: best K of this work item so far
+
+    while (true) {
+        __syncthreads();
+        if (tid == 0) *s_item = atomicAdd(a.counter, 1);
+        __syncthreads();
+        const int64_t item_id = *s_item;
+        if (item_id >= n_items) break;
+        const int q = (int)(item_id / C), c = (int)(item_id % C);
+        const int64_t qb = a.q_indptr[q];
+        const int nq = (int)(a.q_indptr[q + 1] - qb);
+        const float theta_run = a.run_theta[q];
+        // threshold-on-update needs a full running list to test against
+        const bool update_mode = (a.mode == 2) && (theta_run > 0.f);
+        if (warp == 0) item.reset();
+        if (tid == 0) *s_thr = fmaxf(theta_run, PR_DENORM_MIN);
+        const int tile0 = (a.chunk0 + c) * a.tiles_per_item;
+
+        // an empty query scores nothing: its list stays empty and is zero-filled at the end
+        const int n_tiles_item = nq > 0 ? a.tiles_per_item : 0;
+        for (int ts = 0; ts < n_tiles_item; ++ts) {
+            const int64_t tile_lo64 = (int64_t)(tile0 + ts) * T;
+            if (tile_lo64 >= a.n_docs) break;
+            const int tile_lo = (int)tile_lo64;
+            const int tile_n = min(T, a.n_docs - tile_lo);
+            const int tile_hi = tile_lo + tile_n;
+            if (tid == 0) *s_cand_n = 0;
+
+            for (int p0 = 0; p0 < nq; p0 += kMaxPassTerms) {
+                const int np = min(kMaxPassTerms, nq - p0);
+                const bool carry = (nq <= kMaxPassTerms) && (ts > 0);
+                // ---- plan: posting range of every term of this pass inside the tile
+                for (int j = warp; j < np; j += NW) {
+                    const int32_t t = a.q_terms[qb + p0 + j];
+                    int64_t b = 0, e = 0;
+                    if (t < 0 || t >= a.n_terms) {
+                        if (lane == 0) atomicOr(a.status, 1);
+                    } else {
+                        const int64_t b0 = a.indptr[t], e0 = a.indptr[t + 1];
+                        if (e0 - b0 <= kLightDf) {
+                            b = b0;  // short list: take it whole, RMW filters by doc range
+                            e = e0;
+                        } else {
+                            b = carry ? seg_e[j]
+                                      : pr_lower_bound_warp(a.doc_ids, b0, e0, tile_lo, lane);
+                            int64_t lim = b + tile_n;  // a tile holds <= tile_n postings of a term
+                            if (lim > e0) lim = e0;
+                            e = pr_lower_bound_warp(a.doc_ids, b, lim, tile_hi, lane);
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        seg_b[j] = b;
+                        seg_e[j] = e;
+                    }
+                }
+                __syncthreads();
+                const float thr_push = update_mode ? *((volatile float *)s_thr) : __int_as_float(0x7f800000);
+
+                // ---- scatter-accumulate, one term at a time (fp32, query-token order)
+                for (int j = 0; j < np; ++j) {
+                    const int64_t b = seg_b[j], e = seg_e[j];
+                    if (e <= b) continue;  // uniform: same shared-memory values for all threads
+                    for (int64_t i = (b & ~(int64_t)3) + 4 * (int64_t)tid; i < e; i += 4 * NT) {
+                        int4 dd;
+                        float4 ww;
+                        if (i + 4 <= a.nnz) {
+                            dd = pr_ldg_stream_i4(a.doc_ids + i);
+                            ww = pr_ldg_stream_f4(a.weights + i);
+                        } else {
+                            dd.x = i + 0 < a.nnz ? a.doc_ids[i + 0] : -1;
+                            dd.y = i + 1 < a.nnz ? a.doc_ids[i + 1] : -1;
+                            dd.z = i + 2 < a.nnz ? a.doc_ids[i + 2] : -1;
+                            dd.w = -1;
+                            ww.x = i + 0 < a.nnz ? a.weights[i + 0] : 0.f;
+                            ww.y = i + 1 < a.nnz ? a.weights[i + 1] : 0.f;
+                            ww.z = i + 2 < a.nnz ? a.weights[i + 2] : 0.f;
+                            ww.w = 0.f;
+                        }
+                        const unsigned o0 = (unsigned)(dd.x - tile_lo), o1 = (unsigned)(dd.y - tile_lo);
+                        const unsigned o2 = (unsigned)(dd.z - tile_lo), o3 = (unsigned)(dd.w - tile_lo);
+                        const bool m0 = (i + 0 >= b) && (i + 0 < e) && o0 < (unsigned)tile_n;
+                        const bool m1 = (i + 1 >= b) && (i + 1 < e) && o1 < (unsigned)tile_n;
+                        const bool m2 = (i + 2 >= b) && (i + 2 < e) && o2 < (unsigned)tile_n;
+                        const bool m3 = (i + 3 >= b) && (i + 3 < e) && o3 < (unsigned)tile_n;
+                        // the four documents are distinct (one posting per doc and term):
+                        // load all, add, store all
+                        float v0 = m0 ? tile[o0] : 0.f;
+                        float v1 = m1 ? tile[o1] : 0.f;
+                        float v2 = m2 ? tile[o2] : 0.f;
+                        float v3 = m3 ? tile[o3] : 0.f;
+                        v0 += ww.x;
+                        v1 += ww.y;
+                        v2 += ww.z;
+                        v3 += ww.w;
+                        if (m0) tile[o0] = v0;
+                        if (m1) tile[o1] = v1;
+                        if (m2) tile[o2] = v2;
+                        if (m3) tile[o3] = v3;
+                        if ((m0 && v0 >= thr_push) || (m1 && v1 >= thr_push) ||
+                            (m2 && v2 >= thr_push) || (m3 && v3 >= thr_push)) {
+                            const unsigned oo[4] = {o0, o1, o2, o3};
+                            const float vv[4] = {v0, v1, v2, v3};
+                            const bool mm[4] = {m0, m1, m2, m3};
+#pragma unroll
+                            for (int x = 0; x < 4; ++x)
+                                if (mm[x] && vv[x] >= thr_push &&
+                                    *((volatile int32_t *)s_cand_n) < a.cand_cap) {
+                                    const int pos = atomicAdd(s_cand_n, 1);
+                                    if (pos < a.cand_cap) cand_off[pos] = (int32_t)oo[x];
+                                }
+                        }
+                    }
+                    __syncthreads();
+                }
+                __syncthreads();  // plan arrays are rewritten by the next pass / tile
+            }
+
+            // ---- select from the finished tile
+            const int cand_n = *((volatile int32_t *)s_cand_n);
+            const bool scan = !update_mode || cand_n >= a.cand_cap;
+            if (!scan) {
+                if (cand_n > 0) {
+                    for (int i = tid; i < cand_n; i += NT)
+                        cand_s[i] = atomicExch(&tile[cand_off[i]], 0.f);  // duplicates read 0
+                    __syncthreads();
+                    if (warp == 0) {
+                        float thr = *((volatile float *)s_thr);
+                        float ks;
+                        int kd;
+                        item.kth(K, ks, kd);
+                        for (int base = 0; base < cand_n; base += 32) {
+                            const int i = base + lane;
+                            const float cs = i < cand_n ? cand_s[i] : -1.f;
+                            const int cd = i < cand_n ? tile_lo + cand_off[i] + a.doc_id_base : 0;
+                            unsigned m = __ballot_sync(PR_FULL_MASK, cs >= thr);
+                            while (m) {
+                                const int l = __ffs(m) - 1;
+                                m &= m - 1;
+                                const float bs = __shfl_sync(PR_FULL_MASK, cs, l);
+                                const int bd = __shfl_sync(PR_FULL_MASK, cd, l);
+                                if (bs > theta_run && pr_beats(bs, bd, ks, kd)) {
+                                    item.insert(bs, bd, lane);
+                                    item.kth(K, ks, kd);
+                                    thr = fmaxf(thr, ks);
+                                }
+                            }
+                        }
+                        if (lane == 0) *s_thr = thr;
+                    }
+                }
+                for (int v = tid; v < nv; v += NT) tile4[v] = zero4;
+            } else {
+                WarpTopK<E> wl;
+                wl.reset();
+                int nins = 0;
+                float thr_w = *((volatile float *)s_thr);
+                float ks = PR_SENT_SCORE;
+                int kd = PR_SENT_DOC;
+                for (int v = tid; v < nv; v += NT) {
+                    const float4 x = tile4[v];
+                    tile4[v] = zero4;
+                    const bool any = (x.x >= thr_w) || (x.y >= thr_w) || (x.z >= thr_w) || (x.w >= thr_w);
+                    if (__any_sync(PR_FULL_MASK, any)) {
+                        const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {
+                            unsigned m = __ballot_sync(PR_FULL_MASK, xs[cc] >= thr_w);
+                            while (m) {
+                                const int l = __ffs(m) - 1;
+                                m &= m - 1;
+                                const float bs = __shfl_sync(PR_FULL_MASK, xs[cc], l);
+                                const int bd = tile_lo + a.doc_id_base + 4 * (v - lane + l) + cc;
+                                if (bs > theta_run && pr_beats(bs, bd, ks, kd)) {
+                                    wl.insert(bs, bd, lane);
+                                    ++nins;
+                                    wl.kth(K, ks, kd);
+                                    thr_w = fmaxf(thr_w, ks);
+                                }
+                            }
+                        }
+                    }
+                }
+                const int nvalid = min(nins, K);
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int i = e * 32 + lane;
+                    if (i < nvalid) {
+                        wl_s[warp * K + i] = wl.s[e];
+                        wl_d[warp * K + i] = wl.d[e];
+                    }
+                }
+                if (lane == 0) wl_n[warp] = nvalid;
+                __syncthreads();
+                if (warp == 0) {
+                    float thr = *((volatile float *)s_thr);
+                    float iks;
+                    int ikd;
+                    item.kth(K, iks, ikd);
+                    for (int w = 0; w < NW; ++w) {
+                        const int n = wl_n[w];
+                        for (int i = 0; i < n; ++i) {
+                            const float bs = wl_s[w * K + i];
+                            const int bd = wl_d[w * K + i];
+                            if (!pr_beats(bs, bd, iks, ikd)) break;  // the list is sorted: the rest lose too
+                            item.insert(bs, bd, lane);
+                            item.kth(K, iks, ikd);
+                        }
+                    }
+                    thr = fmaxf(thr, iks);
+                    if (lane == 0) *s_thr = thr;
+                }
+            }
+            __syncthreads();
+        }
+
+        if (warp == 0) {
+            float *ps = a.part_s + ((size_t)q * C + c) * K;
+            int32_t *pd = a.part_d + ((size_t)q * C + c) * K;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int i = e * 32 + lane;
+                if (i < K) {
+                    ps[i] = item.s[e];
+                    pd[i] = item.d[e];
+                }
+            }
+        }
+    }
+}
+
+// One warp per query: running list  <-  running list  U  the C per-item lists of one launch.
+// `finalize` also writes the caller's output, filling a short list with the shard's lowest
+// doc ids at score 0 (canonical zero-score tail).
+template <int E>
+__global__ void __launch_bounds__(128) bm25_merge_kernel(
+    const float *__restrict__ part_s, const int32_t *__restrict__ part_d, int C,
+    int64_t stride_q, int64_t stride_c, float *run_s, int32_t *run_d, float *run_theta, int B,
+    int K, int finalize, float *out_s, int32_t *out_d, int doc_id_base, int n_docs)
+{
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= B) return;
+    WarpTopK<E> L;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = e * 32 + lane;
+        L.s[e] = (run_s && i < K) ? run_s[(size_t)q * K + i] : PR_SENT_SCORE;
+        L.d[e] = (run_d && i < K) ? run_d[(size_t)q * K + i] : PR_SENT_DOC;
+    }
+    float ks;
+    int kd;
+    L.kth(K, ks, kd);
+    for (int c = 0; c < C; ++c) {
+        const float *ps = part_s + q * stride_q + c * stride_c;
+        const int32_t *pd = part_d + q * stride_q + c * stride_c;
+        for (int i = 0; i < K; ++i) {
+            const float bs = ps[i];
+            const int bd = pd[i];
+            if (bs < 0.f || bd < 0) break;           // empty slot / missing entry: list ends
+            if (!pr_beats(bs, bd, ks, kd)) break;    // sorted: the rest lose too
+            L.insert(bs, bd, lane);
+            L.kth(K, ks, kd);
+        }
+    }
+    if (run_s) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int i = e * 32 + lane;
+            if (i < K) {
+                run_s[(size_t)q * K + i] = L.s[e];
+                run_d[(size_t)q * K + i] = L.d[e];
+            }
+        }
+        if (lane == 0) run_theta[q] = ks;
+    }
+    if (finalize) {
+        int nvalid = 0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int i = e * 32 + lane;
+            const bool valid = i < K && L.s[e] >= 0.f;
+            nvalid += __popc(__ballot_sync(PR_FULL_MASK, valid));
+            if (i < K) {
+                out_s[(size_t)q * K + i] = valid ? L.s[e] : -INFINITY;
+                out_d[(size_t)q * K + i] = valid ? L.d[e] : -1;
+            }
+        }
+        __syncwarp();
+        if (n_docs >= 0 && nvalid < K && lane == 0) {
+            // zero-score tail: lowest local doc ids not already listed
+            int cand = 0;
+            for (int pos = nvalid; pos < K; ++pos) {
+                while (cand < n_docs) {
+                    bool listed = false;
+                    for (int i = 0; i < nvalid; ++i)
+                        if (out_d[(size_t)q * K + i] == cand + doc_id_base) listed = true;
+                    if (!listed) break;
+                    ++cand;
+                }
+                if (cand >= n_docs) break;
+                out_s[(size_t)q * K + pos] = 0.f;
+                out_d[(size_t)q * K + pos] = cand + doc_id_base;
+                ++cand;
+            }
+        }
+    }
+}
+
+__global__ void bm25_init_kernel(float *run_s, int32_t *run_d, float *run_theta, int64_t n_run,
+                                 int B, int32_t *counters, int n_counters, int32_t *status)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_run) {
+        run_s[i] = PR_SENT_SCORE;
+        run_d[i] = PR_SENT_DOC;
+    }
+    if (i < B) run_theta[i] = PR_SENT_SCORE;
+    if (i < n_counters) counters[i] = 0;
+    if (i == 0) *status = 0;
+}
+
+// index validation (pr_index_create): indptr monotone and consistent, doc ids in range and
+// strictly ascending inside a term, weights finite and >= 0.
+__global__ void bm25_validate_kernel(const int64_t *indptr, const int32_t *doc_ids,
+                                     const float *weights, int n_terms, int64_t nnz, int n_docs,
+                                     int32_t *bad)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t t = i0; t < n_terms; t += stride) {
+        const int64_t b = indptr[t], e = indptr[t + 1];
+        if (b > e || b < 0 || e > nnz) atomicOr(bad, 1);
+    }
+    if (i0 == 0 && (indptr[0] != 0 || indptr[n_terms] != nnz)) atomicOr(bad, 1);
+    for (int64_t p = i0; p < nnz; p += stride) {
+        const int32_t d = doc_ids[p];
+        const float w = weights[p];
+        if (d < 0 || d >= n_docs) atomicOr(bad, 2);
+        if (!(w >= 0.f) || w > 3.0e38f) atomicOr(bad, 8);
+        if (p > 0 && d <= doc_ids[p - 1]) {
+            // a descent is only legal where a new term's list starts: p must be in indptr
+            int64_t lo = 0, hi = n_terms;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (indptr[mid] < p) lo = mid + 1;
+                else hi = mid;
+            }
+            if (indptr[lo] != p) atomicOr(bad, 4);
+        }
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ host
+struct pr_index {
+    int device;
+    int64_t n_docs_global;
+    int32_t doc_id_base, n_docs, n_terms;
+    int64_t nnz;
+    const int64_t *indptr;
+    const int32_t *doc_ids;
+    const float *weights;
+    pr_bm25_tuning_t tuning;
+    int num_sms;
+    int64_t last_launches;
+    // optional per-kernel timing (pr_index_set_profiling): events around every score launch
+    int profiling;
+    std::vector<cudaEvent_t> ev;   // start/stop pairs
+    int ev_used;
+};
+
+namespace {
+
+struct Layout {
+    int n_chunks, C, L;
+    size_t off_status, off_counters, off_theta, off_run_s, off_run_d, off_part_s, off_part_d, total;
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+Layout make_layout(const pr_index *ix, int32_t B, int32_t K)
+{
+    const pr_bm25_tuning_t &t = ix->tuning;
+    Layout l;
+    const int64_t n_tiles = ((int64_t)ix->n_docs + t.tile_docs - 1) / t.tile_docs;
+    l.n_chunks = (int)((n_tiles + t.tiles_per_item - 1) / t.tiles_per_item);
+    int64_t c = B > 0 ? ((int64_t)t.min_items + B - 1) / B : 1;
+    if (c < 1) c = 1;
+    if (c > l.n_chunks) c = l.n_chunks > 0 ? l.n_chunks : 1;
+    l.C = (int)c;
+    l.L = l.n_chunks > 0 ? (l.n_chunks + l.C - 1) / l.C : 0;
+    size_t o = 0;
+    l.off_status = o;   o = align_up(o + 64, 256);
+    l.off_counters = o; o = align_up(o + (size_t)(l.L + 1) * 4, 256);
+    l.off_theta = o;    o = align_up(o + (size_t)B * 4, 256);
+    l.off_run_s = o;    o = align_up(o + (size_t)B * K * 4, 256);
+    l.off_run_d = o;    o = align_up(o + (size_t)B * K * 4, 256);
+    l.off_part_s = o;   o = align_up(o + (size_t)B * l.C * K * 4, 256);
+    l.off_part_d = o;   o = align_up(o + (size_t)B * l.C * K * 4, 256);
+    l.total = o;
+    return l;
+}
+
+typedef void (*score_fn_t)(const ScoreArgs);
+
+template <int NT, int MINB>
+score_fn_t pick_score(int E)
+{
+    if (E == 1) return bm25_score_kernel<NT, 1, MINB>;
+    if (E == 2) return bm25_score_kernel<NT, 2, MINB>;
+    return bm25_score_kernel<NT, 4, MINB>;
+}
+
+score_fn_t pick_score_fn(int threads, int E)
+{
+    if (threads == 256) return pick_score<256, 4>(E);
+    if (threads == 1024) return pick_score<1024, 1>(E);
+    return pick_score<512, 2>(E);
+}
+
+int launch_merge(int E, dim3 grid, cudaStream_t st, const float *ps, const int32_t *pd, int C,
+                 int64_t sq, int64_t sc, float *rs, int32_t *rd, float *rt, int B, int K, int fin,
+                 float *os, int32_t *od, int base, int n_docs)
+{
+    if (E == 1) bm25_merge_kernel<1><<<grid, 128, 0, st>>>(ps, pd, C, sq, sc, rs, rd, rt, B, K, fin, os, od, base, n_docs);
+    else if (E == 2) bm25_merge_kernel<2><<<grid, 128, 0, st>>>(ps, pd, C, sq, sc, rs, rd, rt, B, K, fin, os, od, base, n_docs);
+    else bm25_merge_kernel<4><<<grid, 128, 0, st>>>(ps, pd, C, sq, sc, rs, rd, rt, B, K, fin, os, od, base, n_docs);
+    PR_CUDA_CHECK(cudaGetLastError());
+    return PR_OK;
+}
+
+void default_tuning(pr_bm25_tuning_t *t)
+{
+    t->tile_docs = 24576;
+    t->tiles_per_item = 4;
+    t->threads = 512;
+    t->mode = 2;
+    t->min_items = 2048;
+    t->cand_cap = 1024;
+}
+
+int check_tuning(const pr_bm25_tuning_t &t)
+{
+    if (t.threads != 256 && t.threads != 512 && t.threads != 1024) {
+        pr_set_error("tuning.threads must be 256, 512 or 1024 (got %d)", t.threads);
+        return PR_EINVAL;
+    }
+    if (t.tile_docs <= 0 || t.tile_docs % (4 * t.threads) != 0) {
+        pr_set_error("tuning.tile_docs must be a positive multiple of 4*threads (got %d)", t.tile_docs);
+        return PR_EINVAL;
+    }
+    if (t.tiles_per_item < 1 || (t.mode != 1 && t.mode != 2) || t.min_items < 1 || t.cand_cap < 32) {
+        pr_set_error("bad tuning (tiles_per_item=%d mode=%d min_items=%d cand_cap=%d)",
+                     t.tiles_per_item, t.mode, t.min_items, t.cand_cap);
+        return PR_EINVAL;
+    }
+    if (score_smem_bytes(t.tile_docs, t.cand_cap, t.threads / 32, PR_MAX_K) > 227 * 1024) {
+        pr_set_error("tuning needs more than 227 KB of shared memory per CTA");
+        return PR_EINVAL;
+    }
+    return PR_OK;
+}
+
+}  // namespace
+
+extern "C" int pr_index_create(pr_index_t **out, int device, int64_t n_docs_global,
+                               int32_t doc_id_base, int32_t n_docs, int32_t n_terms, int64_t nnz,
+                               const int64_t *indptr_dev, const int32_t *doc_ids_dev,
+                               const float *weights_dev)
+{
+    if (!out || !indptr_dev || n_docs < 0 || n_terms < 0 || nnz < 0 || n_docs_global < n_docs ||
+        doc_id_base < 0 || (nnz > 0 && (!doc_ids_dev || !weights_dev))) {
+        pr_set_error("pr_index_create: bad argument");
+        return PR_EINVAL;
+    }
+    if (((uintptr_t)doc_ids_dev & 15) || ((uintptr_t)weights_dev & 15)) {
+        pr_set_error("pr_index_create: doc_ids_dev and weights_dev must be 16-byte aligned");
+        return PR_EINVAL;
+    }
+    if ((int64_t)doc_id_base + n_docs > 0x7fffffffLL) {
+        pr_set_error("pr_index_create: global doc ids exceed int32");
+        return PR_EINVAL;
+    }
+    PR_CUDA_CHECK(cudaSetDevice(device));
+    int32_t *bad = nullptr;
+    int32_t h_bad = 0;
+    // one-time validation scratch; freed before returning (not on the query path)
+    PR_CUDA_CHECK(cudaMalloc(&bad, 4));
+    cudaError_t e = cudaMemset(bad, 0, 4);
+    if (e == cudaSuccess) {
+        bm25_validate_kernel<<<1184, 256>>>(indptr_dev, doc_ids_dev, weights_dev, n_terms, nnz, n_docs, bad);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(&h_bad, bad, 4, cudaMemcpyDeviceToHost);
+    cudaFree(bad);
+    if (e != cudaSuccess) {
+        pr_set_error("pr_index_create: validation failed to run: %s", cudaGetErrorString(e));
+        return PR_ECUDA;
+    }
+    if (h_bad) {
+        pr_set_error("pr_index_create: invalid index (%s%s%s%s)", (h_bad & 1) ? "indptr not monotone/consistent; " : "",
+                     (h_bad & 2) ? "doc id outside [0, n_docs); " : "",
+                     (h_bad & 4) ? "doc ids not ascending within a term; " : "",
+                     (h_bad & 8) ? "weight negative or not finite; " : "");
+        return PR_EINVAL;
+    }
+    pr_index *ix = new pr_index();
+    ix->device = device;
+    ix->n_docs_global = n_docs_global;
+    ix->doc_id_base = doc_id_base;
+    ix->n_docs = n_docs;
+    ix->n_terms = n_terms;
+    ix->nnz = nnz;
+    ix->indptr = indptr_dev;
+    ix->doc_ids = doc_ids_dev;
+    ix->weights = weights_dev;
+    ix->last_launches = 0;
+    ix->profiling = 0;
+    ix->ev_used = 0;
+    default_tuning(&ix->tuning);
+    cudaDeviceProp prop;
+    PR_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    ix->num_sms = prop.multiProcessorCount;
+    *out = ix;
+    return PR_OK;
+}
+
+extern "C" int pr_index_destroy(pr_index_t *index)
+{
+    if (index)
+        for (cudaEvent_t e : index->ev) cudaEventDestroy(e);
+    delete index;
+    return PR_OK;
+}
+
+extern "C" int pr_index_set_profiling(pr_index_t *index, int enable)
+{
+    if (!index) {
+        pr_set_error("pr_index_set_profiling: null index");
+        return PR_EINVAL;
+    }
+    index->profiling = enable ? 1 : 0;
+    index->ev_used = 0;
+    return PR_OK;
+}
+
+extern "C" int pr_bm25_profile(pr_index_t *index, float *score_ms, int32_t *score_launches)
+{
+    if (!index || !score_ms || !score_launches) {
+        pr_set_error("pr_bm25_profile: null argument");
+        return PR_EINVAL;
+    }
+    float total = 0.f;
+    for (int i = 0; i + 1 < index->ev_used; i += 2) {
+        PR_CUDA_CHECK(cudaEventSynchronize(index->ev[i + 1]));
+        float ms = 0.f;
+        PR_CUDA_CHECK(cudaEventElapsedTime(&ms, index->ev[i], index->ev[i + 1]));
+        total += ms;
+    }
+    *score_ms = total;
+    *score_launches = index->ev_used / 2;
+    return PR_OK;
+}
+
+extern "C" int pr_index_set_tuning(pr_index_t *index, const pr_bm25_tuning_t *tuning)
+{
+    if (!index || !tuning) {
+        pr_set_error("pr_index_set_tuning: null argument");
+        return PR_EINVAL;
+    }
+    pr_bm25_tuning_t t = index->tuning;
+    if (tuning->tile_docs) t.tile_docs = tuning->tile_docs;
+    if (tuning->tiles_per_item) t.tiles_per_item = tuning->tiles_per_item;
+    if (tuning->threads) t.threads = tuning->threads;
+    if (tuning->mode) t.mode = tuning->mode;
+    if (tuning->min_items) t.min_items = tuning->min_items;
+    if (tuning->cand_cap) t.cand_cap = tuning->cand_cap;
+    const int rc = check_tuning(t);
+    if (rc != PR_OK) return rc;
+    index->tuning = t;
+    return PR_OK;
+}
+
+extern "C" int pr_index_get_tuning(const pr_index_t *index, pr_bm25_tuning_t *tuning)
+{
+    if (!index || !tuning) {
+        pr_set_error("pr_index_get_tuning: null argument");
+        return PR_EINVAL;
+    }
+    *tuning = index->tuning;
+    return PR_OK;
+}
+
+extern "C" size_t pr_bm25_workspace_bytes(const pr_index_t *index, int32_t n_queries, int32_t k)
+{
+    if (!index || n_queries < 0 || k < 1 || k > PR_MAX_K) return 0;
+    return make_layout(index, n_queries, k).total;
+}
+
+extern "C" int64_t pr_bm25_last_launches(const pr_index_t *index) { return index ? index->last_launches : 0; }
+
+extern "C" int pr_bm25_topk(pr_index_t *index, int32_t n_queries, const int64_t *q_indptr_dev,
+                            const int32_t *q_terms_dev, int32_t k, float *out_scores_dev,
+                            int32_t *out_doc_ids_dev, void *workspace_dev, size_t workspace_bytes,
+                            pr_stream_t stream)
+{
+    if (!index || n_queries < 0 || !q_indptr_dev || !out_scores_dev || !out_doc_ids_dev || !workspace_dev) {
+        pr_set_error("pr_bm25_topk: bad argument");
+        return PR_EINVAL;
+    }
+    if (k < 1 || k > PR_MAX_K) {
+        pr_set_error("pr_bm25_topk: k must be in [1, %d] (got %d)", PR_MAX_K, k);
+        return PR_EINVAL;
+    }
+    if ((int64_t)k > index->n_docs_global) {
+        pr_set_error("k of %d is larger than the number of documents %lld", k, (long long)index->n_docs_global);
+        return PR_ERANGE;
+    }
+    const Layout l = make_layout(index, n_queries, k);
+    if (workspace_bytes < l.total) {
+        pr_set_error("pr_bm25_topk: workspace of %zu bytes, need %zu", workspace_bytes, l.total);
+        return PR_EWORKSPACE;
+    }
+    index->last_launches = 0;
+    index->ev_used = 0;
+    if (n_queries == 0) return PR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const pr_bm25_tuning_t &t = index->tuning;
+    const int E = k <= 32 ? 1 : (k <= 64 ? 2 : 4);
+    unsigned char *ws = (unsigned char *)workspace_dev;
+    int32_t *status = (int32_t *)(ws + l.off_status);
+    int32_t *counters = (int32_t *)(ws + l.off_counters);
+    float *theta = (float *)(ws + l.off_theta);
+    float *run_s = (float *)(ws + l.off_run_s);
+    int32_t *run_d = (int32_t *)(ws + l.off_run_d);
+    float *part_s = (float *)(ws + l.off_part_s);
+    int32_t *part_d = (int32_t *)(ws + l.off_part_d);
+
+    const int64_t n_run = (int64_t)n_queries * k;
+    int64_t n_init = n_run > l.L + 1 ? n_run : l.L + 1;
+    bm25_init_kernel<<<(unsigned)((n_init + 255) / 256), 256, 0, st>>>(run_s, run_d, theta, n_run, n_queries,
+                                                                       counters, l.L + 1, status);
+    PR_CUDA_CHECK(cudaGetLastError());
+    index->last_launches++;
+
+    const int nw = t.threads / 32;
+    const size_t smem = score_smem_bytes(t.tile_docs, t.cand_cap, nw, k);
+    score_fn_t fn = pick_score_fn(t.threads, E);
+    PR_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    PR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, t.threads, smem));
+    if (occ < 1) {
+        pr_set_error("pr_bm25_topk: kernel does not fit (threads=%d smem=%zu)", t.threads, smem);
+        return PR_EINVAL;
+    }
+    const dim3 mgrid((unsigned)((n_queries + 3) / 4));
+
+    ScoreArgs a;
+    a.indptr = index->indptr;
+    a.doc_ids = index->doc_ids;
+    a.weights = index->weights;
+    a.q_indptr = q_indptr_dev;
+    a.q_terms = q_terms_dev;
+    a.run_theta = theta;
+    a.part_s = part_s;
+    a.part_d = part_d;
+    a.status = status;
+    a.nnz = index->nnz;
+    a.n_docs = index->n_docs;
+    a.n_terms = index->n_terms;
+    a.doc_id_base = index->doc_id_base;
+    a.n_queries = n_queries;
+    a.K = k;
+    a.tile_docs = t.tile_docs;
+    a.tiles_per_item = t.tiles_per_item;
+    a.cand_cap = t.cand_cap;
+
+    if (l.L == 0) {  // shard without documents: only the (empty) finalisation
+        return launch_merge(E, mgrid, st, part_s, part_d, 0, 0, 0, run_s, run_d, theta, n_queries, k, 1,
+                            out_scores_dev, out_doc_ids_dev, index->doc_id_base, index->n_docs);
+    }
+    for (int li = 0; li < l.L; ++li) {
+        const int Cl = (li + 1) * l.C <= l.n_chunks ? l.C : l.n_chunks - li * l.C;
+        a.chunk0 = li * l.C;
+        a.n_chunks_launch = Cl;
+        a.counter = counters + li;
+        a.mode = li == 0 ? 1 : t.mode;
+        const int64_t items = (int64_t)n_queries * Cl;
+        int64_t grid = (int64_t)occ * index->num_sms;
+        if (grid > items) grid = items;
+        if (index->profiling) {
+            while ((int)index->ev.size() < index->ev_used + 2) {
+                cudaEvent_t ev;
+                PR_CUDA_CHECK(cudaEventCreate(&ev));
+                index->ev.push_back(ev);
+            }
+            PR_CUDA_CHECK(cudaEventRecord(index->ev[index->ev_used], st));
+        }
+        fn<<<(unsigned)grid, t.threads, smem, st>>>(a);
+        PR_CUDA_CHECK(cudaGetLastError());
+        if (index->profiling) {
+            PR_CUDA_CHECK(cudaEventRecord(index->ev[index->ev_used + 1], st));
+            index->ev_used += 2;
+        }
+        const int rc = launch_merge(E, mgrid, st, part_s, part_d, Cl, (int64_t)Cl * k, k, run_s, run_d, theta,
+                                    n_queries, k, li == l.L - 1, out_scores_dev, out_doc_ids_dev,
+                                    index->doc_id_base, index->n_docs);
+        if (rc != PR_OK) return rc;
+        index->last_launches += 2;
+    }
+    return PR_OK;
+}
+
+extern "C" int pr_bm25_status(const void *workspace_dev, pr_stream_t stream)
+{
+    if (!workspace_dev) {
+        pr_set_error("pr_bm25_status: null workspace");
+        return PR_EINVAL;
+    }
+    int32_t h = 0;
+    PR_CUDA_CHECK(cudaMemcpyAsync(&h, workspace_dev, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    PR_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    if (h & 1) {
+        pr_set_error("query term id outside [0, n_terms)");
+        return PR_ERANGE;
+    }
+    return PR_OK;
+}
+
+extern "C" int pr_topk_merge(int32_t n_queries, int32_t k, int32_t n_lists, const float *scores_dev,
+                             const int32_t *ids_dev, float *out_scores_dev, int32_t *out_ids_dev,
+                             pr_stream_t stream)
+{
+    if (n_queries < 0 || n_lists < 1 || !scores_dev || !ids_dev || !out_scores_dev || !out_ids_dev) {
+        pr_set_error("pr_topk_merge: bad argument");
+        return PR_EINVAL;
+    }
+    if (k < 1 || k > PR_MAX_K) {
+        pr_set_error("pr_topk_merge: k must be in [1, %d] (got %d)", PR_MAX_K, k);
+        return PR_EINVAL;
+    }
+    if (n_queries == 0) return PR_OK;
+    const int E = k <= 32 ? 1 : (k <= 64 ? 2 : 4);
+    // lists are [n_lists, n_queries, k]: query stride k, list stride n_queries*k
+    return launch_merge(E, dim3((unsigned)((n_queries + 3) / 4)), (cudaStream_t)stream, scores_dev, ids_dev,
+                        n_lists, k, (int64_t)n_queries * k, nullptr, nullptr, nullptr, n_queries, k, 1,
+                        out_scores_dev, out_ids_dev, 0, -1);
+}

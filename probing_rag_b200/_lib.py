@@ -20,7 +20,8 @@ c_i32, c_i64, c_f32, c_vp, c_sz = ctypes.c_int32, ctypes.c_int64, ctypes.c_float
 
 class Tuning(ctypes.Structure):
     _fields_ = [("tile_docs", c_i32), ("tiles_per_item", c_i32), ("threads", c_i32),
-                ("mode", c_i32), ("min_items", c_i32), ("cand_cap", c_i32)]
+                ("mode", c_i32), ("min_items", c_i32), ("cand_cap", c_i32),
+                ("subs_per_item", c_i32), ("warps_per_cta", c_i32), ("docs_per_launch", c_i32)]
 
 
 class ProberWeights(ctypes.Structure):
@@ -38,6 +39,9 @@ SIGNATURES = {
     "pr_index_create": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_int, c_i64, c_i32, c_i32, c_i32, c_i64,
                                        c_vp, c_vp, c_vp]),
     "pr_index_destroy": (ctypes.c_int, [c_vp]),
+    "pr_index_aux_bytes": (c_sz, [c_vp, c_sz]),
+    "pr_index_build_aux": (ctypes.c_int, [c_vp, c_vp, c_sz, c_vp]),
+    "pr_index_aux_info": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i32), ctypes.POINTER(c_i64)]),
     "pr_index_set_tuning": (ctypes.c_int, [c_vp, ctypes.POINTER(Tuning)]),
     "pr_index_get_tuning": (ctypes.c_int, [c_vp, ctypes.POINTER(Tuning)]),
     "pr_bm25_workspace_bytes": (c_sz, [c_vp, c_i32, c_i32]),

@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "bm25_warp.cuh"
 
 namespace {
 
@@ -458,6 +459,11 @@ struct pr_index {
     int profiling;
     std::vector<cudaEvent_t> ev;   // start/stop pairs
     int ev_used;
+    // tables of the warp-autonomous kernel (pr_index_build_aux), in caller-owned memory
+    const int32_t *heavy_row;
+    const uint32_t *tp;
+    int32_t n_rows, n_sub;
+    int64_t heavy_min_df;
 };
 
 namespace {
@@ -473,9 +479,16 @@ Layout make_layout(const pr_index *ix, int32_t B, int32_t K)
 {
     const pr_bm25_tuning_t &t = ix->tuning;
     Layout l;
-    const int64_t n_tiles = ((int64_t)ix->n_docs + t.tile_docs - 1) / t.tile_docs;
-    l.n_chunks = (int)((n_tiles + t.tiles_per_item - 1) / t.tiles_per_item);
     int64_t c = B > 0 ? ((int64_t)t.min_items + B - 1) / B : 1;
+    if (t.mode >= 3) {
+        l.n_chunks = (ix->n_sub + t.subs_per_item - 1) / t.subs_per_item;
+        const int64_t chunk_docs = (int64_t)t.subs_per_item * prw::kSub;
+        const int64_t c2 = (t.docs_per_launch + chunk_docs - 1) / chunk_docs;
+        if (c2 > c) c = c2;
+    } else {
+        const int64_t n_tiles = ((int64_t)ix->n_docs + t.tile_docs - 1) / t.tile_docs;
+        l.n_chunks = (int)((n_tiles + t.tiles_per_item - 1) / t.tiles_per_item);
+    }
     if (c < 1) c = 1;
     if (c > l.n_chunks) c = l.n_chunks > 0 ? l.n_chunks : 1;
     l.C = (int)c;
@@ -509,6 +522,23 @@ score_fn_t pick_score_fn(int threads, int E)
     return pick_score<512, 2>(E);
 }
 
+typedef void (*warp_fn_t)(const prw::WarpArgs);
+
+template <int NW>
+warp_fn_t pick_warp(int E)
+{
+    if (E == 1) return prw::bm25_warp_kernel<NW, 1>;
+    if (E == 2) return prw::bm25_warp_kernel<NW, 2>;
+    return prw::bm25_warp_kernel<NW, 4>;
+}
+
+warp_fn_t pick_warp_fn(int nw, int E)
+{
+    if (nw == 4) return pick_warp<4>(E);
+    if (nw == 16) return pick_warp<16>(E);
+    return pick_warp<8>(E);
+}
+
 int launch_merge(int E, dim3 grid, cudaStream_t st, const float *ps, const int32_t *pd, int C,
                  int64_t sq, int64_t sc, float *rs, int32_t *rd, float *rt, int B, int K, int fin,
                  float *os, int32_t *od, int base, int n_docs)
@@ -528,6 +558,9 @@ void default_tuning(pr_bm25_tuning_t *t)
     t->mode = 2;
     t->min_items = 2048;
     t->cand_cap = 1024;
+    t->subs_per_item = 12;
+    t->warps_per_cta = 8;
+    t->docs_per_launch = 98304;
 }
 
 int check_tuning(const pr_bm25_tuning_t &t)
@@ -540,7 +573,13 @@ int check_tuning(const pr_bm25_tuning_t &t)
         pr_set_error("tuning.tile_docs must be a positive multiple of 4*threads (got %d)", t.tile_docs);
         return PR_EINVAL;
     }
-    if (t.tiles_per_item < 1 || (t.mode != 1 && t.mode != 2) || t.min_items < 1 || t.cand_cap < 32) {
+    if (t.subs_per_item < 1 || t.docs_per_launch < 1 ||
+        (t.warps_per_cta != 4 && t.warps_per_cta != 8 && t.warps_per_cta != 16)) {
+        pr_set_error("bad tuning (subs_per_item=%d docs_per_launch=%d warps_per_cta=%d; warps_per_cta is 4, 8 or 16)",
+                     t.subs_per_item, t.docs_per_launch, t.warps_per_cta);
+        return PR_EINVAL;
+    }
+    if (t.tiles_per_item < 1 || t.mode < 1 || t.mode > 4 || t.min_items < 1 || t.cand_cap < 32) {
         pr_set_error("bad tuning (tiles_per_item=%d mode=%d min_items=%d cand_cap=%d)",
                      t.tiles_per_item, t.mode, t.min_items, t.cand_cap);
         return PR_EINVAL;
@@ -608,6 +647,11 @@ extern "C" int pr_index_create(pr_index_t **out, int device, int64_t n_docs_glob
     ix->last_launches = 0;
     ix->profiling = 0;
     ix->ev_used = 0;
+    ix->heavy_row = nullptr;
+    ix->tp = nullptr;
+    ix->n_rows = 0;
+    ix->n_sub = (int32_t)(((int64_t)n_docs + prw::kSub - 1) >> prw::kSubShift);
+    ix->heavy_min_df = 0;
     default_tuning(&ix->tuning);
     cudaDeviceProp prop;
     PR_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
@@ -621,6 +665,75 @@ extern "C" int pr_index_destroy(pr_index_t *index)
     if (index)
         for (cudaEvent_t e : index->ev) cudaEventDestroy(e);
     delete index;
+    return PR_OK;
+}
+
+extern "C" size_t pr_index_aux_bytes(const pr_index_t *index, size_t table_budget_bytes)
+{
+    if (!index) return 0;
+    // heavy_row[n_terms] + block counts + row_term/tp within the budget
+    const size_t fixed = align_up((size_t)index->n_terms * 4, 256) + align_up(((size_t)index->n_terms / 1024 + 2) * 4, 256) + 256;
+    return fixed + align_up(table_budget_bytes, 256);
+}
+
+extern "C" int pr_index_build_aux(pr_index_t *index, void *aux_dev, size_t aux_bytes, pr_stream_t stream)
+{
+    if (!index || !aux_dev) {
+        pr_set_error("pr_index_build_aux: null argument");
+        return PR_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nt = index->n_terms;
+    const int n_blocks = (nt + 1023) / 1024;
+    unsigned char *p = (unsigned char *)aux_dev;
+    size_t o = 0;
+    int32_t *heavy_row = (int32_t *)(p + o);  o = align_up(o + (size_t)nt * 4, 256);
+    int32_t *block_cnt = (int32_t *)(p + o);  o = align_up(o + ((size_t)nt / 1024 + 2) * 4, 256);
+    int32_t *count = (int32_t *)(p + o);      o += 256;
+    if (o > aux_bytes) {
+        pr_set_error("pr_index_build_aux: aux buffer of %zu bytes, need at least %zu", aux_bytes, o);
+        return PR_EWORKSPACE;
+    }
+    const size_t table_bytes = aux_bytes - o;
+    const size_t per_row = ((size_t)index->n_sub + 1) * 4 + 4;   // tp row + row_term entry
+    // smallest df threshold (doubling from kLightDf) whose table fits the budget
+    int64_t min_df = prw::kLightDf;
+    int32_t rows = 0;
+    for (;;) {
+        PR_CUDA_CHECK(cudaMemsetAsync(count, 0, 4, st));
+        if (nt > 0) prw::count_heavy_kernel<<<296, 256, 0, st>>>(index->indptr, nt, min_df, count);
+        PR_CUDA_CHECK(cudaGetLastError());
+        PR_CUDA_CHECK(cudaMemcpyAsync(&rows, count, 4, cudaMemcpyDeviceToHost, st));
+        PR_CUDA_CHECK(cudaStreamSynchronize(st));
+        if ((size_t)rows * per_row + 512 <= table_bytes || rows == 0) break;
+        min_df *= 2;
+    }
+    int32_t *row_term = (int32_t *)(p + o);   o = align_up(o + (size_t)(rows > 0 ? rows : 1) * 4, 256);
+    uint32_t *tp = (uint32_t *)(p + o);
+    if (nt > 0) {
+        prw::heavy_block_count_kernel<<<n_blocks, 1024, 0, st>>>(index->indptr, nt, min_df, block_cnt);
+        prw::heavy_block_scan_kernel<<<1, 32, 0, st>>>(block_cnt, n_blocks);
+        prw::heavy_assign_kernel<<<n_blocks, 1024, 0, st>>>(index->indptr, nt, min_df, block_cnt, heavy_row, row_term);
+        if (rows > 0)
+            prw::tp_fill_kernel<<<2368, 256, 0, st>>>(index->indptr, index->doc_ids, row_term, rows, index->n_sub, tp);
+    }
+    PR_CUDA_CHECK(cudaGetLastError());
+    PR_CUDA_CHECK(cudaStreamSynchronize(st));
+    index->heavy_row = heavy_row;
+    index->tp = tp;
+    index->n_rows = rows;
+    index->heavy_min_df = min_df;
+    return PR_OK;
+}
+
+extern "C" int pr_index_aux_info(const pr_index_t *index, int32_t *n_rows, int64_t *min_df)
+{
+    if (!index || !n_rows || !min_df) {
+        pr_set_error("pr_index_aux_info: null argument");
+        return PR_EINVAL;
+    }
+    *n_rows = index->n_rows;
+    *min_df = index->heavy_min_df;
     return PR_OK;
 }
 
@@ -666,6 +779,9 @@ extern "C" int pr_index_set_tuning(pr_index_t *index, const pr_bm25_tuning_t *tu
     if (tuning->mode) t.mode = tuning->mode;
     if (tuning->min_items) t.min_items = tuning->min_items;
     if (tuning->cand_cap) t.cand_cap = tuning->cand_cap;
+    if (tuning->subs_per_item) t.subs_per_item = tuning->subs_per_item;
+    if (tuning->warps_per_cta) t.warps_per_cta = tuning->warps_per_cta;
+    if (tuning->docs_per_launch) t.docs_per_launch = tuning->docs_per_launch;
     const int rc = check_tuning(t);
     if (rc != PR_OK) return rc;
     index->tuning = t;
@@ -734,14 +850,30 @@ extern "C" int pr_bm25_topk(pr_index_t *index, int32_t n_queries, const int64_t 
     PR_CUDA_CHECK(cudaGetLastError());
     index->last_launches++;
 
-    const int nw = t.threads / 32;
-    const size_t smem = score_smem_bytes(t.tile_docs, t.cand_cap, nw, k);
-    score_fn_t fn = pick_score_fn(t.threads, E);
-    PR_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool warp_mode = t.mode >= 3;
+    if (warp_mode && (!index->heavy_row || (index->n_rows > 0 && !index->tp))) {
+        pr_set_error("pr_bm25_topk: tuning.mode %d needs the index tables: call pr_index_build_aux first", t.mode);
+        return PR_EINVAL;
+    }
+    const int nw = warp_mode ? t.warps_per_cta : t.threads / 32;
+    const int threads = nw * 32;
+    const size_t smem = warp_mode ? prw::warp_smem_bytes(nw) : score_smem_bytes(t.tile_docs, t.cand_cap, nw, k);
+    score_fn_t fn = nullptr;
+    warp_fn_t wfn = nullptr;
+    const void *kfn = nullptr;
+    if (warp_mode) {
+        wfn = pick_warp_fn(nw, E);
+        kfn = (const void *)wfn;
+    } else {
+        fn = pick_score_fn(t.threads, E);
+        kfn = (const void *)fn;
+    }
+    PR_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PR_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int occ = 0;
-    PR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, t.threads, smem));
+    PR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, threads, smem));
     if (occ < 1) {
-        pr_set_error("pr_bm25_topk: kernel does not fit (threads=%d smem=%zu)", t.threads, smem);
+        pr_set_error("pr_bm25_topk: kernel does not fit (threads=%d smem=%zu)", threads, smem);
         return PR_EINVAL;
     }
     const dim3 mgrid((unsigned)((n_queries + 3) / 4));
@@ -766,19 +898,37 @@ extern "C" int pr_bm25_topk(pr_index_t *index, int32_t n_queries, const int64_t 
     a.tiles_per_item = t.tiles_per_item;
     a.cand_cap = t.cand_cap;
 
+    prw::WarpArgs w;
+    w.indptr = index->indptr;
+    w.doc_ids = index->doc_ids;
+    w.weights = index->weights;
+    w.heavy_row = index->heavy_row;
+    w.tp = index->tp;
+    w.q_indptr = q_indptr_dev;
+    w.q_terms = q_terms_dev;
+    w.run_theta = theta;
+    w.part_s = part_s;
+    w.part_d = part_d;
+    w.status = status;
+    w.nnz = index->nnz;
+    w.n_docs = index->n_docs;
+    w.n_terms = index->n_terms;
+    w.doc_id_base = index->doc_id_base;
+    w.n_queries = n_queries;
+    w.K = k;
+    w.n_sub = index->n_sub;
+    w.subs_per_item = t.subs_per_item;
+
     if (l.L == 0) {  // shard without documents: only the (empty) finalisation
         return launch_merge(E, mgrid, st, part_s, part_d, 0, 0, 0, run_s, run_d, theta, n_queries, k, 1,
                             out_scores_dev, out_doc_ids_dev, index->doc_id_base, index->n_docs);
     }
     for (int li = 0; li < l.L; ++li) {
         const int Cl = (li + 1) * l.C <= l.n_chunks ? l.C : l.n_chunks - li * l.C;
-        a.chunk0 = li * l.C;
-        a.n_chunks_launch = Cl;
-        a.counter = counters + li;
-        a.mode = li == 0 ? 1 : t.mode;
         const int64_t items = (int64_t)n_queries * Cl;
         int64_t grid = (int64_t)occ * index->num_sms;
-        if (grid > items) grid = items;
+        const int64_t need = warp_mode ? (items + nw - 1) / nw : items;
+        if (grid > need) grid = need;
         if (index->profiling) {
             while ((int)index->ev.size() < index->ev_used + 2) {
                 cudaEvent_t ev;
@@ -787,7 +937,19 @@ extern "C" int pr_bm25_topk(pr_index_t *index, int32_t n_queries, const int64_t 
             }
             PR_CUDA_CHECK(cudaEventRecord(index->ev[index->ev_used], st));
         }
-        fn<<<(unsigned)grid, t.threads, smem, st>>>(a);
+        if (warp_mode) {
+            w.chunk0 = li * l.C;
+            w.n_chunks_launch = Cl;
+            w.counter = counters + li;
+            w.mode = li == 0 ? 3 : t.mode;  // the first launch has no running k-th score yet
+            wfn<<<(unsigned)grid, threads, smem, st>>>(w);
+        } else {
+            a.chunk0 = li * l.C;
+            a.n_chunks_launch = Cl;
+            a.counter = counters + li;
+            a.mode = li == 0 ? 1 : t.mode;
+            fn<<<(unsigned)grid, threads, smem, st>>>(a);
+        }
         PR_CUDA_CHECK(cudaGetLastError());
         if (index->profiling) {
             PR_CUDA_CHECK(cudaEventRecord(index->ev[index->ev_used + 1], st));

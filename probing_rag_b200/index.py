@@ -84,7 +84,7 @@ class BM25Index:
 
     def __init__(self, indptr: torch.Tensor, doc_ids: torch.Tensor, weights: torch.Tensor,
                  n_docs: int, n_docs_global: int | None = None, doc_id_base: int = 0,
-                 meta: dict | None = None):
+                 meta: dict | None = None, aux_budget_bytes: int | None = None):
         if not torch.cuda.is_available():
             raise RuntimeError("BM25Index needs a CUDA device: the retrieval hot path has no CPU fallback")
         if indptr.device.type != "cuda":
@@ -108,6 +108,14 @@ class BM25Index:
                 ctypes.byref(self._handle), self.device.index or 0, self.n_docs_global, self.doc_id_base,
                 self.n_docs, self.n_terms, self.nnz, self.indptr.data_ptr(),
                 self.doc_ids.data_ptr() if self.nnz else None, self.weights.data_ptr() if self.nnz else None))
+            # tables of the warp-autonomous kernel: posting offsets at every 2048-doc boundary
+            # for the frequent terms, within ~1/4 of the index size (min 16 MB, max 8 GB)
+            budget = aux_budget_bytes if aux_budget_bytes is not None else \
+                int(min(max(self.nnz * 2, 16 << 20), 8 << 30))
+            nbytes = int(L.pr_index_aux_bytes(self._handle, budget))
+            self._aux = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            _lib.check(L.pr_index_build_aux(self._handle, self._aux.data_ptr(), nbytes,
+                                            torch.cuda.current_stream(self.device).cuda_stream))
 
     def __del__(self):
         h = getattr(self, "_handle", None)
@@ -187,6 +195,11 @@ class BM25Index:
         ms, n = ctypes.c_float(), ctypes.c_int32()
         _lib.check(_lib.lib().pr_bm25_profile(self._handle, ctypes.byref(ms), ctypes.byref(n)))
         return float(ms.value), int(n.value)
+
+    def aux_info(self) -> dict:
+        rows, min_df = ctypes.c_int32(), ctypes.c_int64()
+        _lib.check(_lib.lib().pr_index_aux_info(self._handle, ctypes.byref(rows), ctypes.byref(min_df)))
+        return {"tp_rows": int(rows.value), "tp_min_df": int(min_df.value), "aux_bytes": int(self._aux.numel())}
 
     @property
     def last_launches(self) -> int:

@@ -22,7 +22,11 @@ TUNINGS = [
     dict(threads=512, tile_docs=24576, tiles_per_item=4, mode=2),
     dict(threads=512, tile_docs=24576, tiles_per_item=4, mode=1),
     dict(threads=256, tile_docs=8192, tiles_per_item=3, mode=2, min_items=64),
-    dict(threads=1024, tile_docs=49152, tiles_per_item=1, mode=2, cand_cap=32),
+    dict(threads=1024, tile_docs=40960, tiles_per_item=1, mode=2, cand_cap=32),
+    dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304),
+    dict(mode=3, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304),
+    dict(mode=4, subs_per_item=1, warps_per_cta=4, docs_per_launch=2048, min_items=1),      # one sub-tile per item, many launches
+    dict(mode=4, subs_per_item=5, warps_per_cta=16, docs_per_launch=1000000, min_items=100000),  # one launch
     dict(threads=512, tile_docs=2048, tiles_per_item=1, mode=2, min_items=1),   # many launches
     dict(threads=512, tile_docs=16384, tiles_per_item=2, mode=1, min_items=100000),  # one launch
 ]
@@ -75,21 +79,26 @@ def test_config1_100k_docs_1k_queries(small_corpus, corpus_gpu, tun):
 
 @pytest.mark.parametrize("k", [1, 5, 32, 33, 64, 100, 128])
 def test_depth_sweep(small_corpus, corpus_gpu, k):
-    corpus_gpu.set_tuning(threads=512, tile_docs=24576, tiles_per_item=4, mode=2, min_items=2048, cand_cap=1024)
     qi, qt = small_corpus["q_indptr"][:65], small_corpus["q_terms"]
     os_, od = co.retrieve_batch(small_corpus["index"], qi, qt, k, n_threads=8)
-    gs, gd = run_gpu(corpus_gpu, qi, qt, k)
-    assert_parity(gs, gd, os_, od)
+    for tun in (dict(threads=512, tile_docs=24576, tiles_per_item=4, mode=2, min_items=2048, cand_cap=1024),
+                dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
+                dict(mode=3, subs_per_item=3, warps_per_cta=8, docs_per_launch=20000, min_items=2048)):
+        corpus_gpu.set_tuning(**tun)
+        gs, gd = run_gpu(corpus_gpu, qi, qt, k)
+        assert_parity(gs, gd, os_, od)
 
 
 @pytest.mark.parametrize("nq", [1, 2, 37])
 def test_small_batches(small_corpus, corpus_gpu, nq):
     """The reference's own shape: one query at a time (exp_rag.py:426)."""
-    corpus_gpu.set_tuning(threads=512, tile_docs=24576, tiles_per_item=4, mode=2, min_items=2048, cand_cap=1024)
     qi, qt = small_corpus["q_indptr"][:nq + 1], small_corpus["q_terms"]
     os_, od = co.retrieve_batch(small_corpus["index"], qi, qt, 10)
-    gs, gd = run_gpu(corpus_gpu, qi, qt, 10)
-    assert_parity(gs, gd, os_, od)
+    for tun in (dict(threads=512, tile_docs=24576, tiles_per_item=4, mode=2, min_items=2048, cand_cap=1024),
+                dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048)):
+        corpus_gpu.set_tuning(**tun)
+        gs, gd = run_gpu(corpus_gpu, qi, qt, 10)
+        assert_parity(gs, gd, os_, od)
 
 
 def test_long_transcript_queries(small_corpus, corpus_gpu):
@@ -99,8 +108,9 @@ def test_long_transcript_queries(small_corpus, corpus_gpu):
     qi, qt = synth.queries_np(48, small_corpus["vocab"], idx["df"], kind="later")
     assert np.diff(qi).max() > 256
     os_, od = co.retrieve_batch(idx, qi, qt, 10, n_threads=8)
-    for mode in (1, 2):
-        corpus_gpu.set_tuning(threads=512, tile_docs=24576, tiles_per_item=2, mode=mode, min_items=2048)
+    for mode in (1, 2, 3, 4):
+        corpus_gpu.set_tuning(threads=512, tile_docs=24576, tiles_per_item=2, mode=mode, min_items=2048,
+                              subs_per_item=4, warps_per_cta=8, docs_per_launch=98304)
         gs, gd = run_gpu(corpus_gpu, qi, qt, 10)
         assert_parity(gs, gd, os_, od)
 
@@ -118,7 +128,7 @@ def test_edge_queries(small_corpus, corpus_gpu):
     qi[1:] = np.cumsum([len(q) for q in queries])
     qt = np.array([t for q in queries for t in q], dtype=np.int32)
     os_, od = bo.retrieve_batch(idx, qi, qt, 10)
-    for tun in TUNINGS[:3]:
+    for tun in TUNINGS[:3] + TUNINGS[4:8]:
         corpus_gpu.set_tuning(**tun)
         gs, gd = run_gpu(corpus_gpu, qi, qt, 10)
         assert_parity(gs, gd, os_, od)
@@ -168,7 +178,10 @@ def test_tie_heavy_corpus():
         os_, od = bo.retrieve_batch(idx, qi, qt, k)
         for tun in (dict(threads=256, tile_docs=4096, tiles_per_item=2, mode=2, min_items=1),
                     dict(threads=256, tile_docs=4096, tiles_per_item=2, mode=1, min_items=100000),
-                    dict(threads=512, tile_docs=24576, tiles_per_item=1, mode=2, cand_cap=32)):
+                    dict(threads=512, tile_docs=24576, tiles_per_item=1, mode=2, cand_cap=32),
+                    dict(mode=4, subs_per_item=2, warps_per_cta=4, docs_per_launch=4096, min_items=1),
+                    dict(mode=3, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=100000),
+                    dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048)):
             gi.set_tuning(**tun)
             gs, gd = run_gpu(gi, qi, qt, k)
             assert_parity(gs, gd, os_, od)
@@ -191,6 +204,7 @@ def test_doc_range_shards_and_merge_equal_single_index(small_corpus, corpus_gpu)
             sh = bo.build_index(toks[off[lo]:off[hi]], lens[lo:hi], small_corpus["vocab"], n_docs_global=n_docs,
                                 avgdl_global=idx["avgdl"], df_global=idx["df"], doc_id_base=lo)
             gi = gpu_index(sh, n_docs_global=n_docs, doc_id_base=lo)
+            gi.set_tuning(mode=4 if g != 3 else 2)
             dev = gi.device
             s, d = gi.topk(torch.from_numpy(qi).to(dev), torch.from_numpy(qt).to(dev), 10)
             ss.append(s); dd.append(d)
@@ -258,11 +272,12 @@ def test_full_size_21m_properties():
     gi, qi, qt = bench.build_workload(synth.N_DOCS_WIKI, 1 << 22, 2048, torch.device("cuda"))
     dev = gi.device
     d_qi, d_qt = torch.from_numpy(qi).to(dev), torch.from_numpy(qt).to(dev)
-    s2, d2 = gi.topk(d_qi, d_qt, 10)
-    gi.set_tuning(mode=1)
-    s1, d1 = gi.topk(d_qi, d_qt, 10)
     gi.set_tuning(mode=2)
-    assert torch.equal(s1, s2) and torch.equal(d1, d2)
+    s2, d2 = gi.topk(d_qi, d_qt, 10)
+    for mode in (1, 3, 4):
+        gi.set_tuning(mode=mode)
+        s1, d1 = gi.topk(d_qi, d_qt, 10)
+        assert torch.equal(s1, s2) and torch.equal(d1, d2), mode
     assert bool((s2[:, :-1] >= s2[:, 1:]).all())
     tie = s2[:, :-1] == s2[:, 1:]
     assert bool((d2[:, :-1][tie] < d2[:, 1:][tie]).all())

@@ -34,6 +34,10 @@ def main():
     alg = gi.algorithmic_bytes(qi, qt, args.k)
     if args.configs:
         cfgs = [{kv.split("=")[0]: int(kv.split("=")[1]) for kv in c.split(",")} for c in args.configs.split(";")]
+    elif args.grid == "warp":
+        cfgs = [dict(mode=m, subs_per_item=g, warps_per_cta=nw, docs_per_launch=dpl)
+                for m, g, nw, dpl in itertools.product([4, 3], [12, 6, 24], [8, 16, 4], [98304, 49152, 196608])
+                if not (m == 3 and (nw != 8 or dpl != 98304))]
     elif args.grid == "small":
         cfgs = [dict(threads=th, tile_docs=td, tiles_per_item=s, mode=m)
                 for (th, td), s, m in itertools.product(

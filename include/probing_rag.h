@@ -50,7 +50,7 @@ typedef struct pr_bm25_tuning {
     int32_t cand_cap;       /* candidate buffer entries per CTA (mode 2)                      */
     /* warp-autonomous kernel (modes 3 = scan select, 4 = threshold-on-update select) */
     int32_t subs_per_item;  /* consecutive 2048-document sub-tiles one warp scores for one query */
-    int32_t warps_per_cta;  /* 4, 8 or 16                                                      */
+    int32_t warps_per_cta;  /* 4, 8, 9 or 16                                                   */
     int32_t docs_per_launch;/* document range one launch covers for large batches (L2 reuse)   */
 } pr_bm25_tuning_t;
 
@@ -62,7 +62,8 @@ const char *pr_last_error(void);
  * (/root/reference/exp_rag.py:242), term-major with ascending doc ids:
  *   indptr_dev  int64[n_terms+1], doc_ids_dev int32[nnz] (LOCAL ids, 0-based, ascending per
  *   term), weights_dev float[nnz] (>= 0; precomputed idf*tfc).  doc_ids_dev and weights_dev
- *   must be 16-byte aligned.  n_docs is this shard's document count, doc_id_base the global
+ *   must be 16-byte aligned and readable up to nnz rounded up to a multiple of 4 elements
+ *   (the kernels use 128-bit loads; what lies past nnz is ignored).  n_docs is this shard's document count, doc_id_base the global
  *   id of local doc 0, n_docs_global the whole corpus size (k is checked against it).
  * Validates the arrays on the device and synchronises once. */
 int pr_index_create(pr_index_t **out, int device, int64_t n_docs_global, int32_t doc_id_base,

@@ -535,6 +535,7 @@ warp_fn_t pick_warp(int E)
 warp_fn_t pick_warp_fn(int nw, int E)
 {
     if (nw == 4) return pick_warp<4>(E);
+    if (nw == 9) return pick_warp<9>(E);
     if (nw == 16) return pick_warp<16>(E);
     return pick_warp<8>(E);
 }
@@ -574,8 +575,8 @@ int check_tuning(const pr_bm25_tuning_t &t)
         return PR_EINVAL;
     }
     if (t.subs_per_item < 1 || t.docs_per_launch < 1 ||
-        (t.warps_per_cta != 4 && t.warps_per_cta != 8 && t.warps_per_cta != 16)) {
-        pr_set_error("bad tuning (subs_per_item=%d docs_per_launch=%d warps_per_cta=%d; warps_per_cta is 4, 8 or 16)",
+        (t.warps_per_cta != 4 && t.warps_per_cta != 8 && t.warps_per_cta != 9 && t.warps_per_cta != 16)) {
+        pr_set_error("bad tuning (subs_per_item=%d docs_per_launch=%d warps_per_cta=%d; warps_per_cta is 4, 8, 9 or 16)",
                      t.subs_per_item, t.docs_per_launch, t.warps_per_cta);
         return PR_EINVAL;
     }

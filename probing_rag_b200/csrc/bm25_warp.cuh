@@ -141,78 +141,65 @@ __global__ void __launch_bounds__(NW * 32) bm25_warp_kernel(const WarpArgs a)
                 const int np = min(32, nq - p0);
                 if (!single) load_info(p0, np, sub_lo, sub_lo + sub_n);
                 int32_t sb = 0, se = 0;
-                bool filt = false;
                 if (lane < np && t_ok) {
                     if (t_row >= 0) {
                         const uint32_t *r = a.tp + (size_t)t_row * tp_stride + g;
                         sb = (int32_t)__ldg(r);
                         se = (int32_t)__ldg(r + 1);
                     } else {
-                        sb = t_lb;
+                        sb = t_lb;  // not tabulated: item-level range, filtered by doc range below
                         se = t_le;
-                        filt = true;
                     }
                 }
+                const float thr_push = update_mode ? thr : __int_as_float(0x7f800000);
                 for (int j = 0; j < np; ++j) {
                     const int32_t b = __shfl_sync(PR_FULL_MASK, sb, j);
                     const int32_t e = __shfl_sync(PR_FULL_MASK, se, j);
                     if (e <= b) continue;  // warp-uniform
                     const int64_t B = __shfl_sync(PR_FULL_MASK, t_b0, j) + b;
-                    const bool f = __shfl_sync(PR_FULL_MASK, (int)filt, j) != 0;
                     const int head = (int)(B & 3);
+                    const int len = e - b;
+                    const int total = head + len;
+                    const int lastgrp = (total - 1) & ~3;  // last 4-aligned group holding a posting
+                    // the arrays are readable up to nnz rounded up to 4 (pr_index_create contract)
                     const int32_t *pd = a.doc_ids + (B - head);
                     const float *pw = a.weights + (B - head);
-                    const int total = head + (e - b);
-                    const int64_t room64 = a.nnz - (B - head);
-                    const int room = room64 > 0x7fffffff ? 0x7fffffff : (int)room64;
                     for (int i0 = 0; i0 < total; i0 += 128) {
                         const int i = i0 + 4 * lane;
-                        int4 dd = make_int4(-1, -1, -1, -1);
-                        float4 ww = zero4;
-                        if (i < total) {
-                            if (i + 4 <= room) {
-                                dd = pr_ldg_stream_i4(pd + i);
-                                ww = pr_ldg_stream_f4(pw + i);
-                            } else {
-                                if (i + 0 < room) { dd.x = pd[i + 0]; ww.x = pw[i + 0]; }
-                                if (i + 1 < room) { dd.y = pd[i + 1]; ww.y = pw[i + 1]; }
-                                if (i + 2 < room) { dd.z = pd[i + 2]; ww.z = pw[i + 2]; }
-                            }
-                        }
+                        // lanes past the segment re-read its last group; their elements are masked
+                        const int ic = min(i, lastgrp);
+                        const int4 dd = pr_ldg_stream_i4(pd + ic);
+                        const float4 ww = pr_ldg_stream_f4(pw + ic);
                         const int ds[4] = {dd.x, dd.y, dd.z, dd.w};
                         const float wv[4] = {ww.x, ww.y, ww.z, ww.w};
+                        const int r = i - head;
                         unsigned o[4];
                         bool m[4];
                         float v[4];
 #pragma unroll
                         for (int x = 0; x < 4; ++x) {
-                            const int idx = i + x;
-                            const unsigned off = (unsigned)(ds[x] - sub_lo);
-                            m[x] = idx >= head && idx < total && off < (unsigned)sub_n;
-                            o[x] = off & (kSub - 1);
+                            m[x] = (unsigned)(r + x) < (unsigned)len && (unsigned)(ds[x] - sub_lo) < (unsigned)sub_n;
+                            o[x] = (unsigned)ds[x] & (kSub - 1);  // sub_lo is a multiple of kSub
                         }
                         // distinct documents (one posting per doc and term): load all, add, store all
 #pragma unroll
-                        for (int x = 0; x < 4; ++x) v[x] = m[x] ? tile[o[x]] : 0.f;
-#pragma unroll
-                        for (int x = 0; x < 4; ++x) v[x] += wv[x];
+                        for (int x = 0; x < 4; ++x) v[x] = tile[o[x]] + wv[x];
 #pragma unroll
                         for (int x = 0; x < 4; ++x)
                             if (m[x]) tile[o[x]] = v[x];
-                        if (update_mode) {
+                        const bool hit = (m[0] && v[0] >= thr_push) || (m[1] && v[1] >= thr_push) ||
+                                         (m[2] && v[2] >= thr_push) || (m[3] && v[3] >= thr_push);
+                        if (__any_sync(PR_FULL_MASK, hit)) {  // rare: remember candidates
 #pragma unroll
                             for (int x = 0; x < 4; ++x) {
-                                const bool hit = m[x] && v[x] >= thr;
-                                const unsigned pm = __ballot_sync(PR_FULL_MASK, hit);
-                                if (pm) {
-                                    const int slot = cnt + __popc(pm & lt_mask);
-                                    if (hit && slot < kWarpCand) cand[slot] = (int32_t)o[x];
-                                    cnt += __popc(pm);
-                                }
+                                const bool h = m[x] && v[x] >= thr_push;
+                                const unsigned pm = __ballot_sync(PR_FULL_MASK, h);
+                                const int slot = cnt + __popc(pm & lt_mask);
+                                if (h && slot < kWarpCand) cand[slot] = (int32_t)o[x];
+                                cnt += __popc(pm);
                             }
                         }
                     }
-                    (void)f;
                     __syncwarp();  // order this term's stores before the next term's loads
                 }
             }

@@ -90,8 +90,15 @@ class BM25Index:
         if indptr.device.type != "cuda":
             raise ValueError("index arrays must live on a CUDA device")
         self.indptr = indptr.to(torch.int64).contiguous()
-        self.doc_ids = doc_ids.to(torch.int32).contiguous()
-        self.weights = weights.to(torch.float32).contiguous()
+        # 128-bit loads: keep the posting arrays readable up to nnz rounded up to 4 elements
+        nnz = doc_ids.numel()
+
+        def padded(t, dtype):
+            buf = torch.zeros((nnz + 3) // 4 * 4 + 4, dtype=dtype, device=t.device)
+            buf[:nnz] = t
+            return buf[:nnz]
+        self.doc_ids = padded(doc_ids, torch.int32)
+        self.weights = padded(weights, torch.float32)
         self.n_docs = int(n_docs)
         self.n_docs_global = int(n_docs if n_docs_global is None else n_docs_global)
         self.doc_id_base = int(doc_id_base)

@@ -52,6 +52,7 @@ typedef struct pr_bm25_tuning {
     int32_t subs_per_item;  /* consecutive 2048-document sub-tiles one warp scores for one query */
     int32_t warps_per_cta;  /* 4, 8, 9 or 16                                                   */
     int32_t docs_per_launch;/* document range one launch covers for large batches (L2 reuse)   */
+    int32_t lazy_zero;      /* 1 = epoch-tagged accumulators, re-zeroed every 7th sub-tile; 2 = off */
 } pr_bm25_tuning_t;
 
 int pr_version(void);

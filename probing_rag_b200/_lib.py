@@ -21,7 +21,8 @@ c_i32, c_i64, c_f32, c_vp, c_sz = ctypes.c_int32, ctypes.c_int64, ctypes.c_float
 class Tuning(ctypes.Structure):
     _fields_ = [("tile_docs", c_i32), ("tiles_per_item", c_i32), ("threads", c_i32),
                 ("mode", c_i32), ("min_items", c_i32), ("cand_cap", c_i32),
-                ("subs_per_item", c_i32), ("warps_per_cta", c_i32), ("docs_per_launch", c_i32)]
+                ("subs_per_item", c_i32), ("warps_per_cta", c_i32), ("docs_per_launch", c_i32),
+                ("lazy_zero", c_i32)]
 
 
 class ProberWeights(ctypes.Structure):

@@ -22,6 +22,8 @@
 //   * launches walk the document range in ascending order, so the part of the index a
 //     launch reads (tens of MB) stays L2-resident across the whole query batch; after each
 //     launch a merge kernel folds the per-item lists into the per-query running top-k.
+#include <string.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -423,11 +425,16 @@ __global__ void bm25_validate_kernel(const int64_t *indptr, const int32_t *doc_i
         if (b > e || b < 0 || e > nnz) atomicOr(bad, 1);
     }
     if (i0 == 0 && (indptr[0] != 0 || indptr[n_terms] != nnz)) atomicOr(bad, 1);
+    uint32_t wmin = 0xffffffffu, wmax = 0u;
     for (int64_t p = i0; p < nnz; p += stride) {
         const int32_t d = doc_ids[p];
         const float w = weights[p];
         if (d < 0 || d >= n_docs) atomicOr(bad, 2);
         if (!(w >= 0.f) || w > 3.0e38f) atomicOr(bad, 8);
+        else {  // non-negative floats order like their bit patterns
+            wmin = min(wmin, __float_as_uint(w));
+            wmax = max(wmax, __float_as_uint(w));
+        }
         if (p > 0 && d <= doc_ids[p - 1]) {
             // a descent is only legal where a new term's list starts: p must be in indptr
             int64_t lo = 0, hi = n_terms;
@@ -438,6 +445,14 @@ __global__ void bm25_validate_kernel(const int64_t *indptr, const int32_t *doc_i
             }
             if (indptr[lo] != p) atomicOr(bad, 4);
         }
+    }
+    for (int o = 16; o; o >>= 1) {
+        wmin = min(wmin, __shfl_xor_sync(PR_FULL_MASK, wmin, o));
+        wmax = max(wmax, __shfl_xor_sync(PR_FULL_MASK, wmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(reinterpret_cast<uint32_t *>(bad) + 1, wmin);
+        atomicMax(reinterpret_cast<uint32_t *>(bad) + 2, wmax);
     }
 }
 
@@ -464,6 +479,7 @@ struct pr_index {
     const uint32_t *tp;
     int32_t n_rows, n_sub;
     int64_t heavy_min_df;
+    bool lazy_ok;
 };
 
 namespace {
@@ -524,20 +540,28 @@ score_fn_t pick_score_fn(int threads, int E)
 
 typedef void (*warp_fn_t)(const prw::WarpArgs);
 
-template <int NW>
+template <int NW, bool LAZY>
 warp_fn_t pick_warp(int E)
 {
-    if (E == 1) return prw::bm25_warp_kernel<NW, 1>;
-    if (E == 2) return prw::bm25_warp_kernel<NW, 2>;
-    return prw::bm25_warp_kernel<NW, 4>;
+    if (E == 1) return prw::bm25_warp_kernel<NW, 1, LAZY>;
+    if (E == 2) return prw::bm25_warp_kernel<NW, 2, LAZY>;
+    return prw::bm25_warp_kernel<NW, 4, LAZY>;
 }
 
-warp_fn_t pick_warp_fn(int nw, int E)
+warp_fn_t pick_warp_fn(int nw, int E, bool lazy)
 {
-    if (nw == 4) return pick_warp<4>(E);
-    if (nw == 9) return pick_warp<9>(E);
-    if (nw == 16) return pick_warp<16>(E);
-    return pick_warp<8>(E);
+    if (lazy) {
+        if (nw == 4) return pick_warp<4, true>(E);
+        if (nw == 9) return pick_warp<9, true>(E);
+        if (nw == 13) return pick_warp<13, true>(E);
+        if (nw == 16) return pick_warp<16, true>(E);
+        return pick_warp<8, true>(E);
+    }
+    if (nw == 4) return pick_warp<4, false>(E);
+    if (nw == 9) return pick_warp<9, false>(E);
+    if (nw == 13) return pick_warp<13, false>(E);
+    if (nw == 16) return pick_warp<16, false>(E);
+    return pick_warp<8, false>(E);
 }
 
 int launch_merge(int E, dim3 grid, cudaStream_t st, const float *ps, const int32_t *pd, int C,
@@ -562,6 +586,7 @@ void default_tuning(pr_bm25_tuning_t *t)
     t->subs_per_item = 12;
     t->warps_per_cta = 8;
     t->docs_per_launch = 98304;
+    t->lazy_zero = 1;
 }
 
 int check_tuning(const pr_bm25_tuning_t &t)
@@ -575,8 +600,8 @@ int check_tuning(const pr_bm25_tuning_t &t)
         return PR_EINVAL;
     }
     if (t.subs_per_item < 1 || t.docs_per_launch < 1 ||
-        (t.warps_per_cta != 4 && t.warps_per_cta != 8 && t.warps_per_cta != 9 && t.warps_per_cta != 16)) {
-        pr_set_error("bad tuning (subs_per_item=%d docs_per_launch=%d warps_per_cta=%d; warps_per_cta is 4, 8, 9 or 16)",
+        (t.warps_per_cta != 4 && t.warps_per_cta != 8 && t.warps_per_cta != 9 && t.warps_per_cta != 13 && t.warps_per_cta != 16)) {
+        pr_set_error("bad tuning (subs_per_item=%d docs_per_launch=%d warps_per_cta=%d; warps_per_cta is 4, 8, 9, 13 or 16)",
                      t.subs_per_item, t.docs_per_launch, t.warps_per_cta);
         return PR_EINVAL;
     }
@@ -614,16 +639,17 @@ extern "C" int pr_index_create(pr_index_t **out, int device, int64_t n_docs_glob
     }
     PR_CUDA_CHECK(cudaSetDevice(device));
     int32_t *bad = nullptr;
-    int32_t h_bad = 0;
+    int32_t h_bad3[3] = {0, -1, 0};  // flags, min weight bits (start at 0xffffffff), max weight bits
     // one-time validation scratch; freed before returning (not on the query path)
-    PR_CUDA_CHECK(cudaMalloc(&bad, 4));
-    cudaError_t e = cudaMemset(bad, 0, 4);
+    PR_CUDA_CHECK(cudaMalloc(&bad, 12));
+    cudaError_t e = cudaMemcpy(bad, h_bad3, 12, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
         bm25_validate_kernel<<<1184, 256>>>(indptr_dev, doc_ids_dev, weights_dev, n_terms, nnz, n_docs, bad);
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaMemcpy(&h_bad, bad, 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(h_bad3, bad, 12, cudaMemcpyDeviceToHost);
     cudaFree(bad);
+    const int32_t h_bad = h_bad3[0];
     if (e != cudaSuccess) {
         pr_set_error("pr_index_create: validation failed to run: %s", cudaGetErrorString(e));
         return PR_ECUDA;
@@ -653,6 +679,12 @@ extern "C" int pr_index_create(pr_index_t **out, int device, int64_t n_docs_glob
     ix->n_rows = 0;
     ix->n_sub = (int32_t)(((int64_t)n_docs + prw::kSub - 1) >> prw::kSubShift);
     ix->heavy_min_df = 0;
+    {   // lazily re-zeroed accumulators need every weight in [2^-30, 2^10] (bm25_warp.cuh)
+        float wmin, wmax;
+        memcpy(&wmin, &h_bad3[1], 4);
+        memcpy(&wmax, &h_bad3[2], 4);
+        ix->lazy_ok = nnz > 0 && wmin >= 9.313225746154785e-10f && wmax <= 1024.f;
+    }
     default_tuning(&ix->tuning);
     cudaDeviceProp prop;
     PR_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
@@ -783,6 +815,7 @@ extern "C" int pr_index_set_tuning(pr_index_t *index, const pr_bm25_tuning_t *tu
     if (tuning->subs_per_item) t.subs_per_item = tuning->subs_per_item;
     if (tuning->warps_per_cta) t.warps_per_cta = tuning->warps_per_cta;
     if (tuning->docs_per_launch) t.docs_per_launch = tuning->docs_per_launch;
+    if (tuning->lazy_zero) t.lazy_zero = tuning->lazy_zero;
     const int rc = check_tuning(t);
     if (rc != PR_OK) return rc;
     index->tuning = t;
@@ -863,7 +896,7 @@ extern "C" int pr_bm25_topk(pr_index_t *index, int32_t n_queries, const int64_t 
     warp_fn_t wfn = nullptr;
     const void *kfn = nullptr;
     if (warp_mode) {
-        wfn = pick_warp_fn(nw, E);
+        wfn = pick_warp_fn(nw, E, index->lazy_ok && t.lazy_zero == 1);
         kfn = (const void *)wfn;
     } else {
         fn = pick_score_fn(t.threads, E);

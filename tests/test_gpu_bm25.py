@@ -25,6 +25,8 @@ TUNINGS = [
     dict(threads=1024, tile_docs=40960, tiles_per_item=1, mode=2, cand_cap=32),
     dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304),
     dict(mode=3, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304),
+    dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, lazy_zero=2),
+    dict(mode=3, subs_per_item=7, warps_per_cta=9, docs_per_launch=98304, lazy_zero=2),
     dict(mode=4, subs_per_item=1, warps_per_cta=4, docs_per_launch=2048, min_items=1),      # one sub-tile per item, many launches
     dict(mode=4, subs_per_item=5, warps_per_cta=16, docs_per_launch=1000000, min_items=100000),  # one launch
     dict(threads=512, tile_docs=2048, tiles_per_item=1, mode=2, min_items=1),   # many launches
@@ -70,7 +72,7 @@ def test_golden_fixture_on_gpu(golden_dir):
 @pytest.mark.parametrize("tun", TUNINGS, ids=lambda t: "-".join(f"{k[:4]}{v}" for k, v in t.items()))
 def test_config1_100k_docs_1k_queries(small_corpus, corpus_gpu, tun):
     """BASELINE config 1: 100k passages, 1,000 queries, top-10, every tuning variant."""
-    corpus_gpu.set_tuning(**tun)
+    corpus_gpu.set_tuning(**dict(dict(lazy_zero=1), **tun))
     qi, qt = small_corpus["q_indptr"], small_corpus["q_terms"]
     os_, od = co.retrieve_batch(small_corpus["index"], qi, qt, 10, n_threads=8)
     gs, gd = run_gpu(corpus_gpu, qi, qt, 10)
@@ -128,7 +130,7 @@ def test_edge_queries(small_corpus, corpus_gpu):
     qi[1:] = np.cumsum([len(q) for q in queries])
     qt = np.array([t for q in queries for t in q], dtype=np.int32)
     os_, od = bo.retrieve_batch(idx, qi, qt, 10)
-    for tun in TUNINGS[:3] + TUNINGS[4:8]:
+    for tun in TUNINGS[:3] + TUNINGS[4:10]:
         corpus_gpu.set_tuning(**tun)
         gs, gd = run_gpu(corpus_gpu, qi, qt, 10)
         assert_parity(gs, gd, os_, od)
@@ -181,8 +183,9 @@ def test_tie_heavy_corpus():
                     dict(threads=512, tile_docs=24576, tiles_per_item=1, mode=2, cand_cap=32),
                     dict(mode=4, subs_per_item=2, warps_per_cta=4, docs_per_launch=4096, min_items=1),
                     dict(mode=3, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=100000),
-                    dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048)):
-            gi.set_tuning(**tun)
+                    dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
+                    dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048, lazy_zero=2)):
+            gi.set_tuning(**dict(dict(lazy_zero=1), **tun))
             gs, gd = run_gpu(gi, qi, qt, k)
             assert_parity(gs, gd, os_, od)
 
@@ -287,3 +290,20 @@ def test_full_size_21m_properties():
             "indptr": gi.indptr.cpu().numpy(), "num_docs": gi.n_docs}
     os_, od = co.retrieve_batch(host, qi[:25], qt, 10, n_threads=min(24, os.cpu_count() or 1))
     assert_parity(s2[:24].cpu().numpy(), d2[:24].cpu().numpy(), os_, od)
+
+
+def test_weights_outside_lazy_range_use_plain_accumulators(small_corpus):
+    """Weights outside [2^-30, 2^10] cannot carry epoch tags (bm25_warp.cuh): the index must
+    fall back to densely re-zeroed accumulators and still match the oracle bit for bit."""
+    idx = dict(small_corpus["index"])
+    data = idx["data"].copy()
+    data[::7] *= np.float32(2.0 ** -40)          # tiny weights
+    data[3::11] *= np.float32(4096.0)            # large weights
+    idx["data"] = data
+    gi = gpu_index(idx)
+    qi, qt = small_corpus["q_indptr"][:129], small_corpus["q_terms"]
+    os_, od = co.retrieve_batch(idx, qi, qt, 10, n_threads=8)
+    for mode in (4, 3, 2):
+        gi.set_tuning(mode=mode)
+        gs, gd = run_gpu(gi, qi, qt, 10)
+        assert_parity(gs, gd, os_, od)

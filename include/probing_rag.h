@@ -45,7 +45,8 @@ typedef struct pr_bm25_tuning {
     int32_t tile_docs;      /* documents per shared-memory score tile (multiple of 4*threads) */
     int32_t tiles_per_item; /* consecutive tiles one CTA scores for one query                 */
     int32_t threads;        /* 256, 512 or 1024                                               */
-    int32_t mode;           /* 1 = full-tile scan select; 2 = threshold-on-update select      */
+    int32_t mode;           /* CTA-cooperative kernel: 1 = scan select, 2 = threshold-on-update; warp-autonomous
+                               kernel (default): 3 = scan select, 4 = threshold-on-update        */
     int32_t min_items;      /* doc ranges are split until a launch has this many work items   */
     int32_t cand_cap;       /* candidate buffer entries per CTA (mode 2)                      */
     /* warp-autonomous kernel (modes 3 = scan select, 4 = threshold-on-update select) */

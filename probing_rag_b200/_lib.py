@@ -9,7 +9,7 @@ import ctypes
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libprobingrag.so")
+LIB_PATH = os.environ.get("PR_LIB_PATH") or os.path.join(PKG_DIR, "libprobingrag.so")   # PR_LIB_PATH: A/B builds
 
 PR_OK, PR_EINVAL, PR_ECUDA, PR_ERANGE, PR_EWORKSPACE, PR_EUNSUPPORTED = 0, -1, -2, -3, -4, -5
 PR_MAX_K = 128

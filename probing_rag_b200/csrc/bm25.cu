@@ -580,13 +580,13 @@ void default_tuning(pr_bm25_tuning_t *t)
     t->tile_docs = 24576;
     t->tiles_per_item = 4;
     t->threads = 512;
-    t->mode = 2;
+    t->mode = 4;
     t->min_items = 2048;
     t->cand_cap = 1024;
     t->subs_per_item = 12;
     t->warps_per_cta = 8;
     t->docs_per_launch = 98304;
-    t->lazy_zero = 1;
+    t->lazy_zero = 2;
 }
 
 int check_tuning(const pr_bm25_tuning_t &t)

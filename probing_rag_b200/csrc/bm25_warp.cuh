@@ -22,9 +22,16 @@
 
 #include "common.cuh"
 
+#ifndef PR_SUB_SHIFT
+#define PR_SUB_SHIFT 11
+#endif
+#ifndef PR_PF
+#define PR_PF 4
+#endif
+
 namespace prw {
 
-constexpr int kSubShift = 11;
+constexpr int kSubShift = PR_SUB_SHIFT;
 constexpr int kSub = 1 << kSubShift;  // documents per warp sub-tile (8 KB of fp32)
 constexpr int kWarpCand = 32;         // candidate slots per warp (threshold-on-update)
 constexpr int kLightDf = 128;         // lists this short are taken whole and range-filtered
@@ -171,7 +178,7 @@ __device__ __forceinline__ void seg_unpack(uint2 d, int64_t &B, int &len)
     len = (int)((d.y >> 8) & 0x7fffffu);
 }
 
-constexpr int kPF = 4;  // segments whose first 64 slots are in flight together
+constexpr int kPF = PR_PF;  // segments whose first 64 slots are in flight together
 
 // One (term, sub-tile) segment whose first 64 slots are already loaded (`first`), then 128
 // slots per step while more than 64 remain, and a 64-slot tail: most segments are short, and

@@ -125,32 +125,38 @@ int pr_topk_merge(int32_t n_queries, int32_t k, int32_t n_lists, const float *sc
  * (/root/reference/exp_rag.py:407-415) + stream compaction of the "retrieve" rows. */
 #define PR_PROBER_MAX 8
 
-typedef struct pr_prober_weights {
-    int32_t d_model;  /* 2048 */
-    int32_t hidden;   /* 512  */
-    /* fp32 vectors, caller-owned device memory (state_dict tensors as they are) */
-    const float *ln_in_w, *ln_in_b; /* [d_model] layer_norm_input.{weight,bias} */
-    const float *b1;                /* [hidden]  fc1.bias                        */
-    const float *ln1_w, *ln1_b;     /* [hidden]  layer_norm1                     */
-    const float *b2;                /* [hidden]  fc2.bias                        */
-    const float *ln2_w, *ln2_b;     /* [hidden]  layer_norm2                     */
-    const float *w3, *b3;           /* [2,hidden], [2]  fc3 (kept fp32)          */
-    /* bf16 matrices, row-major [out, in] like nn.Linear.weight, 128-byte aligned */
-    const void *w1_bf16;            /* [hidden, d_model] */
-    const void *w2_bf16;            /* [hidden, hidden]  */
-} pr_prober_weights_t;
+/* A set of n_probers ImprovedProbe MLPs, packed per prober and kept in caller-owned device
+ * memory.  The fp32 vectors are the state_dict tensors as they are (utils.py:29-57 names in
+ * the comments); the two weight matrices are pre-split for bf16x3 tensor-core accumulation:
+ * hi = bf16(w), lo = bf16(w - hi), each row-major [out, in] like nn.Linear.weight. */
+typedef struct pr_prober_set {
+    int32_t n_probers;               /* <= PR_PROBER_MAX; 6 in the reference (exp_rag.py:311) */
+    int32_t d_model;                 /* 2048 (gemma-2b); multiple of 128, <= 2048             */
+    int32_t hidden;                  /* 512                                                   */
+    const float *ln_in_w, *ln_in_b;  /* [P][d_model]   layer_norm_input.{weight,bias}         */
+    const float *b1;                 /* [P][hidden]    fc1.bias                               */
+    const float *ln1_w, *ln1_b;      /* [P][hidden]    layer_norm1.{weight,bias}              */
+    const float *b2;                 /* [P][hidden]    fc2.bias                               */
+    const float *ln2_w, *ln2_b;      /* [P][hidden]    layer_norm2.{weight,bias}              */
+    const float *w3, *b3;            /* [P][2][hidden], [P][2]   fc3 (kept fp32)              */
+    const void *w1_hi, *w1_lo;       /* bf16 [P][hidden][d_model]  fc1.weight split, 128-byte aligned */
+    const void *w2_hi, *w2_lo;       /* bf16 [P][hidden][hidden]   fc2.weight split, 128-byte aligned */
+} pr_prober_set_t;
 
 size_t pr_prober_workspace_bytes(int32_t n_probers, int32_t n_rows, int32_t d_model, int32_t hidden);
 
-/* X_dev float[n_rows, n_probers, d_model] (pooled hidden states, exp_rag.py:385-386).
- * out_logits_dev float[n_rows, n_probers, 2] (may be NULL), out_probsum_dev float[n_rows, 2],
- * out_retrieve_mask_dev uint8[n_rows] (1 = retrieve), out_compact_idx_dev int32[n_rows]
- * (row indices with mask 1, ascending, first *out_n_retrieve_dev entries valid). */
-int pr_prober_forward(const pr_prober_weights_t *probers, int32_t n_probers, int32_t n_rows,
-                      const float *X_dev, float theta, int32_t ablation, float *out_logits_dev,
-                      float *out_probsum_dev, uint8_t *out_retrieve_mask_dev,
-                      int32_t *out_compact_idx_dev, int32_t *out_n_retrieve_dev,
-                      void *workspace_dev, size_t workspace_bytes, pr_stream_t stream);
+/* X_dev float[n_rows, n_probers, d_model]: pooled hidden states, one per probed layer
+ * (exp_rag.py:385-386).  Outputs: out_logits_dev float[n_rows, n_probers, 2] (may be NULL),
+ * out_probsum_dev float[n_rows, 2] = sum over probers >= ablation of softmax(logits)
+ * (exp_rag.py:407-410), out_retrieve_mask_dev uint8[n_rows] (1 = retrieve, i.e. NOT
+ * probsum[0] + theta < probsum[1], exp_rag.py:414), out_compact_idx_dev int32[n_rows] (indices
+ * of the rows that retrieve, ascending; the first *out_n_retrieve_dev are valid).
+ * workspace_dev must be 1024-byte aligned. */
+int pr_prober_forward(const pr_prober_set_t *probers, int32_t n_rows, const float *X_dev, float theta,
+                      int32_t ablation, float *out_logits_dev, float *out_probsum_dev,
+                      uint8_t *out_retrieve_mask_dev, int32_t *out_compact_idx_dev,
+                      int32_t *out_n_retrieve_dev, void *workspace_dev, size_t workspace_bytes,
+                      pr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -25,12 +25,12 @@ class Tuning(ctypes.Structure):
                 ("lazy_zero", c_i32)]
 
 
-class ProberWeights(ctypes.Structure):
-    _fields_ = [("d_model", c_i32), ("hidden", c_i32),
+class ProberSet(ctypes.Structure):
+    _fields_ = [("n_probers", c_i32), ("d_model", c_i32), ("hidden", c_i32),
                 ("ln_in_w", c_vp), ("ln_in_b", c_vp), ("b1", c_vp),
                 ("ln1_w", c_vp), ("ln1_b", c_vp), ("b2", c_vp),
                 ("ln2_w", c_vp), ("ln2_b", c_vp), ("w3", c_vp), ("b3", c_vp),
-                ("w1_bf16", c_vp), ("w2_bf16", c_vp)]
+                ("w1_hi", c_vp), ("w1_lo", c_vp), ("w2_hi", c_vp), ("w2_lo", c_vp)]
 
 
 # every symbol include/probing_rag.h declares: (restype, argtypes)
@@ -52,6 +52,9 @@ SIGNATURES = {
     "pr_index_set_profiling": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "pr_bm25_profile": (ctypes.c_int, [c_vp, ctypes.POINTER(c_f32), ctypes.POINTER(c_i32)]),
     "pr_topk_merge": (ctypes.c_int, [c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "pr_prober_workspace_bytes": (c_sz, [c_i32, c_i32, c_i32, c_i32]),
+    "pr_prober_forward": (ctypes.c_int, [ctypes.POINTER(ProberSet), c_i32, c_vp, c_f32, c_i32, c_vp, c_vp, c_vp,
+                                         c_vp, c_vp, c_vp, c_sz, c_vp]),
 }
 
 _lib = None

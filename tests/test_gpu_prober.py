@@ -1,0 +1,137 @@
+"""Fused prober (tcgen05 bf16x3 GEMMs + gate + compaction) against the reference's ImprovedProbe.
+Tolerance (BASELINE.json north_star): prober probabilities within 1e-3 of the fp32 reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bm25_oracle as bo
+from oracle import c_oracle as co
+from oracle import prober_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+PROB_ATOL = 1e-3
+
+
+def oracle_probers(layers=po.PROBE_LAYERS, d_model=po.D_MODEL):
+    out = []
+    for layer in layers:
+        p = po.OracleImprovedProbe(d_model, po.N_CLASSES)
+        p.load_state_dict(po.make_prober_state(layer, d_model=d_model))
+        out.append(p.eval())
+    return out
+
+
+@pytest.fixture(scope="module")
+def gate6():
+    from probing_rag_b200.prober import ProberGate
+    probers = oracle_probers()
+    return probers, ProberGate([p.state_dict() for p in probers], device="cuda")
+
+
+def check_gate(out, ref_logits, theta, ablation):
+    psum_ref, ret_ref = po.gate(ref_logits, theta, ablation)
+    assert torch.allclose(out.probsum.cpu(), psum_ref, atol=PROB_ATOL * (ref_logits.shape[1] - ablation) + 1e-6)
+    margin = (psum_ref[:, 0] + theta - psum_ref[:, 1]).abs()
+    agree = (out.retrieve.cpu() == ret_ref) | (margin < 6 * PROB_ATOL)
+    assert bool(agree.all())
+    assert torch.equal(out.retrieve_idx.cpu().long(), torch.nonzero(out.retrieve.cpu()).flatten())
+
+
+def test_golden_reference_outputs(golden_dir, gate6):
+    """tests/golden/prober_golden.npz holds the outputs of the REFERENCE class (utils.py:29-57)."""
+    _, gate = gate6
+    g = np.load(os.path.join(golden_dir, "prober_golden.npz"))
+    x = po.make_hidden_states(int(g["n"]), seed=0)
+    ref = torch.from_numpy(g["logits"])
+    for j, th in enumerate(g["thetas"]):
+        out = gate(x.cuda(), theta=float(th), want_logits=True)
+        dp = (torch.softmax(out.logits.cpu(), -1) - torch.softmax(ref, -1)).abs().max().item()
+        assert dp < PROB_ATOL, dp
+        assert dp < 2e-4, f"bf16x3 should be far inside the tolerance, got {dp}"
+        margin = np.abs(g["probsum"][:, 0] + float(th) - g["probsum"][:, 1])
+        assert np.all((out.retrieve.cpu().numpy() == g["retrieve"][j]) | (margin < 6 * PROB_ATOL))
+
+
+@pytest.mark.parametrize("n", [1, 7, 128, 129, 1000])
+def test_batch_sizes_and_ablation(gate6, n):
+    probers, gate = gate6
+    x = po.make_hidden_states(n, seed=n)
+    ref = po.prober_logits(probers, x)
+    for theta, ablation in ((0.0, 0), (0.5, 2), (-0.25, 5)):
+        out = gate(x.cuda(), theta=theta, ablation=ablation, want_logits=True)
+        assert (torch.softmax(out.logits.cpu(), -1) - torch.softmax(ref, -1)).abs().max().item() < PROB_ATOL
+        check_gate(out, ref, theta, ablation)
+
+
+def test_large_mean_and_scale_inputs(gate6):
+    """Sums of up to 149 residual vectors: large magnitude, non-zero mean (hard parts)."""
+    probers, gate = gate6
+    x = po.make_hidden_states(256, seed=11)
+    x = x * 3.0 + 40.0 * x.std(dim=-1, keepdim=True)
+    ref = po.prober_logits(probers, x)
+    out = gate(x.cuda(), want_logits=True)
+    assert (torch.softmax(out.logits.cpu(), -1) - torch.softmax(ref, -1)).abs().max().item() < PROB_ATOL
+
+
+def test_other_shapes():
+    from probing_rag_b200.prober import ProberGate
+    for d_model, layers in ((256, (6,)), (1024, (6, 8, 10))):
+        probers = oracle_probers(layers, d_model)
+        gate = ProberGate([p.state_dict() for p in probers], device="cuda")
+        x = po.make_hidden_states(300, seed=d_model, n_probers=len(layers), d_model=d_model)
+        ref = po.prober_logits(probers, x)
+        out = gate(x.cuda(), want_logits=True)
+        assert (torch.softmax(out.logits.cpu(), -1) - torch.softmax(ref, -1)).abs().max().item() < PROB_ATOL
+        check_gate(out, ref, 0.0, 0)
+
+
+def test_improved_probe_is_a_drop_in_module(tmp_path):
+    """utils.py:302-330: ImprovedProbe(input_size=d_model, output_size=2).to(device);
+    load_state_dict(torch.load(path)); eval(); prober(x[B,2048]) -> logits[B,2]; .to('cpu')."""
+    from probing_rag_b200.prober import STATE_KEYS, ImprovedProbe
+    sd = po.make_prober_state(12)
+    path = tmp_path / "in3_1.0_gemma-2b_tokens_mean_2_l12_resid_post_ep1.pt"     # utils.py:316 naming
+    torch.save(sd, path)
+    prober = ImprovedProbe(input_size=2048, output_size=2).to("cuda")
+    assert set(prober.state_dict().keys()) == set(STATE_KEYS)
+    assert sum(p.numel() for p in prober.parameters()) == 1318914
+    prober.load_state_dict(torch.load(path))
+    prober.eval()
+    ref = po.OracleImprovedProbe(2048, 2)
+    ref.load_state_dict(sd)
+    ref.eval()
+    x = po.make_hidden_states(5, seed=2)[:, 0]
+    with torch.no_grad():
+        logit = prober(x.cuda())
+        assert logit.shape == (5, 2) and logit.is_cuda
+        want = ref(x)
+        assert (torch.softmax(logit.to("cpu"), -1) - torch.softmax(want, -1)).abs().max().item() < PROB_ATOL
+        one = prober(x[:1].cuda()).to("cpu")                       # the reference's B=1 call (exp_rag.py:387)
+        assert (torch.softmax(one, -1) - torch.softmax(want[:1], -1)).abs().max().item() < PROB_ATOL
+    prober.train()
+    assert prober(x.cuda()).shape == (5, 2)                        # training mode: plain module
+
+
+def test_config4_prober_gated_bm25(small_corpus):
+    """BASELINE config 4 shape: hidden states -> prober -> compacted BM25 top-10."""
+    from probing_rag_b200 import BM25Index, BM25Retriever
+    from probing_rag_b200.prober import ProberGate, gate_and_retrieve
+    idx = small_corpus["index"]
+    gi = BM25Index.from_arrays(idx["data"], idx["indices"], idx["indptr"], idx["num_docs"])
+    retr = BM25Retriever.from_defaults(index=gi, similarity_top_k=10)
+    nq = 512
+    qi, qt = small_corpus["q_indptr"][:nq + 1], small_corpus["q_terms"][:small_corpus["q_indptr"][nq]]
+    probers = oracle_probers()
+    gate = ProberGate([p.state_dict() for p in probers], device="cuda")
+    x = po.make_hidden_states(nq, seed=5)
+    out, scores, ids = gate_and_retrieve(gate, retr, x.cuda(), torch.from_numpy(qi).cuda(), torch.from_numpy(qt).cuda())
+    torch.cuda.synchronize()
+    ref_logits = po.prober_logits(probers, x)
+    check_gate(out, ref_logits, 0.0, 0)
+    sel = out.retrieve_idx.cpu().numpy()
+    assert 0 < len(sel) < nq
+    os_, od = co.retrieve_batch(idx, qi, qt, 10, n_threads=8)
+    assert np.array_equal(ids.cpu().numpy(), od[sel]) and np.array_equal(scores.cpu().numpy(), os_[sel])

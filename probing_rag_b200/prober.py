@@ -159,17 +159,10 @@ def gate_and_retrieve(gate: ProberGate, retriever, X: torch.Tensor, q_indptr: to
     """BASELINE config 4: prober forward -> retrieve/no-retrieve mask -> compacted BM25 top-k.
     Returns (GateOutput, scores f32[n_retrieve, k], doc_ids i32[n_retrieve, k]); row i of the
     results belongs to query out.retrieve_idx[i]."""
+    from .rounds import select_queries
     out = gate(X, theta=theta, ablation=ablation)
-    idx = out.retrieve_idx.long()
-    lens = (q_indptr[1:] - q_indptr[:-1])[idx]
-    c_indptr = torch.zeros(idx.numel() + 1, dtype=torch.int64, device=q_indptr.device)
-    torch.cumsum(lens, 0, out=c_indptr[1:])
-    # gather the surviving queries' term ids (ragged gather via repeat_interleave)
-    starts = q_indptr[:-1][idx]
-    pos = torch.arange(int(c_indptr[-1].item()), device=q_indptr.device) - torch.repeat_interleave(c_indptr[:-1], lens) \
-        + torch.repeat_interleave(starts, lens)
-    c_terms = q_terms[pos]
-    scores, ids = retriever.retrieve_ids(c_indptr, c_terms.to(torch.int32), k)
+    c_indptr, c_terms = select_queries(q_indptr, q_terms, out.retrieve_idx)
+    scores, ids = retriever.retrieve_ids(c_indptr, c_terms, k)
     return out, scores, ids
 
 

@@ -1,0 +1,94 @@
+"""Doc-range sharding of the BM25 index over the GPUs of one box.
+
+The reference is single-process (`exp_rag.py:242`: one BM25Retriever over the whole corpus);
+BM25 shards naturally because a document's score depends only on its own postings and on the
+GLOBAL constants N, avgdl, df.  One process per GPU (torchrun):
+
+    rank g owns docs [g*ceil(N/G), (g+1)*ceil(N/G))                       shard_range
+    df and the token count are summed over ranks once, at build time       global_stats
+    every rank scores the whole query batch against its shard              BM25Index.topk
+    [B,k] (score, doc id) lists are all-gathered                           gather_lists
+    and merged in the canonical order (score desc, doc id asc)             pr_topk_merge
+
+The merged lists equal the single-index lists bit for bit: each document is scored on exactly
+one rank with the same weights and the same fp32 summation order.  The collective plumbing
+below is backend-agnostic (NCCL on the GPUs, gloo in the CPU tests); the scoring and the merge
+are CUDA only (`local_topk` / `merge` are injectable so the host logic can be tested with the
+oracle standing in as the checker).
+"""
+from __future__ import annotations
+
+from typing import Callable
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_docs: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous doc-id range [lo, hi) of `rank`; the last ranks may be short or empty."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world of {world}")
+    per = -(-n_docs // world)
+    return min(rank * per, n_docs), min((rank + 1) * per, n_docs)
+
+
+def _world(group=None) -> int:
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def global_stats(df_local: torch.Tensor, n_tokens_local: int, n_docs_global: int, group=None):
+    """(df_global i64[V], avgdl float): the statistics bm25s computes over the whole corpus
+    (App. A.4), from per-shard counts.  Integer sums, so the result does not depend on the
+    number of shards."""
+    df = df_local.to(torch.int64).clone()
+    n_tok = torch.tensor([int(n_tokens_local)], dtype=torch.int64, device=df.device)
+    if _world(group) > 1:
+        dist.all_reduce(df, group=group)
+        dist.all_reduce(n_tok, group=group)
+    return df, float(n_tok.item()) / float(max(n_docs_global, 1))
+
+
+def gather_lists(scores: torch.Tensor, ids: torch.Tensor, group=None, out=None):
+    """[B,k] per-rank lists -> ([G,B,k] scores, [G,B,k] ids), rank-major."""
+    world = _world(group)
+    if out is None:
+        out = (torch.empty((world,) + tuple(scores.shape), dtype=scores.dtype, device=scores.device),
+               torch.empty((world,) + tuple(ids.shape), dtype=ids.dtype, device=ids.device))
+    if world == 1:
+        out[0][0].copy_(scores)
+        out[1][0].copy_(ids)
+    else:
+        # concatenation along dim 0 ([G*B, k] view): the form every backend accepts
+        flat = (world * scores.shape[0],) + tuple(scores.shape[1:])
+        dist.all_gather_into_tensor(out[0].view(flat), scores.contiguous(), group=group)
+        dist.all_gather_into_tensor(out[1].view(flat), ids.contiguous(), group=group)
+    return out
+
+
+class ShardedBM25:
+    """This rank's shard + the exchange step.  `local_topk(q_indptr, q_terms, k) -> (scores, ids)`
+    defaults to the shard's CUDA kernel, `merge([G,B,k], [G,B,k]) -> ([B,k], [B,k])` to
+    pr_topk_merge."""
+
+    def __init__(self, index=None, group=None, local_topk: Callable | None = None,
+                 merge: Callable | None = None):
+        if index is None and local_topk is None:
+            raise ValueError("pass the shard's BM25Index or a local_topk callable")
+        self.index = index
+        self.group = group
+        self._local = local_topk
+        self._merge = merge
+        self._gath = {}
+
+    def topk(self, q_indptr, q_terms, k: int):
+        if self._local is not None:
+            s, d = self._local(q_indptr, q_terms, k)
+        else:
+            s, d = self.index.topk(q_indptr, q_terms, k, check_status=False)
+        key = (tuple(s.shape), s.device)
+        gs, gd = gather_lists(s, d, self.group, self._gath.get(key))
+        self._gath[key] = (gs, gd)
+        if self._merge is not None:
+            return self._merge(gs, gd)
+        from .index import merge_topk
+        return merge_topk(gs, gd)

@@ -41,9 +41,7 @@ def log(*a):
 
 
 # ----------------------------------------------------------------------------- workload
-def shard_range(n_docs: int, rank: int, world: int):
-    per = -(-n_docs // world)
-    return min(rank * per, n_docs), min((rank + 1) * per, n_docs)
+from probing_rag_b200.sharding import gather_lists, global_stats, shard_range  # noqa: E402
 
 
 def build_workload(n_docs: int, vocab: int, n_queries: int, device, rank: int = 0, world: int = 1,
@@ -72,16 +70,12 @@ def build_workload(n_docs: int, vocab: int, n_queries: int, device, rank: int = 
     tokens = torch.cat(toks) if toks else torch.zeros(0, dtype=torch.int32, device=device)
     doc_lens = torch.cat(lens) if lens else torch.zeros(0, dtype=torch.int32, device=device)
     del toks, lens
-    n_tok = torch.tensor([tokens.numel()], dtype=torch.int64, device=device)
+    n_tok_local = tokens.numel()
     # global statistics
     from probing_rag_b200.index import bm25_weights, count_postings, idf_lucene_table
     term, doc, tf, df_local = count_postings(tokens, doc_lens, vocab)
     del tokens
-    df = df_local.clone()
-    if world > 1:
-        dist.all_reduce(df)
-        dist.all_reduce(n_tok)
-    avgdl = float(n_tok.item()) / float(n_docs)
+    df, avgdl = global_stats(df_local, n_tok_local, n_docs)
     df_host = df.cpu().numpy()
     idf = torch.from_numpy(idf_lucene_table(df_host, n_docs)).to(device)
     w = bm25_weights(term, doc, tf, doc_lens, idf, avgdl)
@@ -234,8 +228,7 @@ def main():
     def step_device():
         gi.topk(d_qi, d_qt, k, out=out, check_status=False)
         if world > 1:
-            dist.all_gather_into_tensor(gath_s, out[0])
-            dist.all_gather_into_tensor(gath_d, out[1])
+            gather_lists(out[0], out[1], out=(gath_s, gath_d))
             return merge_topk(gath_s, gath_d)
         return out
 
@@ -243,8 +236,7 @@ def main():
         s, d, h2d, d2h = gi.topk_host(qi, qt, k)
         if world > 1:
             ds, dd = torch.from_numpy(s).to(device), torch.from_numpy(d).to(device)
-            dist.all_gather_into_tensor(gath_s, ds)
-            dist.all_gather_into_tensor(gath_d, dd)
+            gather_lists(ds, dd, out=(gath_s, gath_d))
             ms, md = merge_topk(gath_s, gath_d)
             s, d = ms.cpu().numpy(), md.cpu().numpy()
         return s, d, h2d, d2h

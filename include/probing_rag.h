@@ -46,12 +46,13 @@ typedef struct pr_bm25_tuning {
     int32_t tiles_per_item; /* consecutive tiles one CTA scores for one query                 */
     int32_t threads;        /* 256, 512 or 1024                                               */
     int32_t mode;           /* CTA-cooperative kernel: 1 = scan select, 2 = threshold-on-update; warp-autonomous
-                               kernel (default): 3 = scan select, 4 = threshold-on-update        */
+                               segment-loop kernel: 3 = scan select, 4 = threshold-on-update; warp-autonomous
+                               flat-step kernel: 5 = scan select, 6 = threshold-on-update        */
     int32_t min_items;      /* doc ranges are split until a launch has this many work items   */
     int32_t cand_cap;       /* candidate buffer entries per CTA (mode 2)                      */
     /* warp-autonomous kernel (modes 3 = scan select, 4 = threshold-on-update select) */
     int32_t subs_per_item;  /* consecutive 2048-document sub-tiles one warp scores for one query */
-    int32_t warps_per_cta;  /* 4, 8, 9 or 16                                                   */
+    int32_t warps_per_cta;  /* 4, 8, 9, 12, 13 or 16 (modes 5/6: 4, 8 or 12)                    */
     int32_t docs_per_launch;/* document range one launch covers for large batches (L2 reuse)   */
     int32_t lazy_zero;      /* 1 = epoch-tagged accumulators, re-zeroed every 7th sub-tile; 2 = off */
 } pr_bm25_tuning_t;
@@ -73,13 +74,18 @@ int pr_index_create(pr_index_t **out, int device, int64_t n_docs_global, int32_t
                     const int32_t *doc_ids_dev, const float *weights_dev);
 int pr_index_destroy(pr_index_t *index);
 
-/* Tables of the warp-autonomous scoring kernel (tuning.mode 3/4), built once per index into
- * caller-owned device memory: heavy_row[n_terms] and, for every term whose df exceeds a
- * threshold chosen so the table fits `table_budget_bytes`, the posting offset of each
- * 2048-document boundary.  pr_index_build_aux synchronises `stream`. */
+/* Per-index structures of the warp-autonomous scoring kernels (tuning.mode >= 3), built once per
+ * index into caller-owned device memory of pr_index_aux_bytes(index, budget) bytes:
+ *   - heavy_row[n_terms] and, for every term whose df exceeds a threshold chosen so the table
+ *     fits a fifth of `table_budget_bytes`, the posting offset of each 2048-document boundary;
+ *   - the hot posting stream (modes 5/6): for the terms with >= 8 postings per 2048 documents, as
+ *     many as fit the rest of the budget, a padded, bank-aware, mask-free copy of their postings
+ *     (about 10 bytes per hot posting).  Without it modes 5/6 read every term from the CSR.
+ * pr_index_build_aux synchronises `stream`. */
 size_t pr_index_aux_bytes(const pr_index_t *index, size_t table_budget_bytes);
 int pr_index_build_aux(pr_index_t *index, void *aux_dev, size_t aux_bytes, pr_stream_t stream);
 int pr_index_aux_info(const pr_index_t *index, int32_t *n_rows, int64_t *min_df);
+int pr_index_hot_info(const pr_index_t *index, int32_t *n_hot, int64_t *min_df, int64_t *stream_bytes);
 int pr_index_set_tuning(pr_index_t *index, const pr_bm25_tuning_t *tuning);
 int pr_index_get_tuning(const pr_index_t *index, pr_bm25_tuning_t *tuning);
 

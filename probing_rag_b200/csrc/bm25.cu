@@ -28,6 +28,7 @@
 
 #include "common.cuh"
 #include "bm25_warp.cuh"
+#include "bm25_flat.cuh"
 
 namespace {
 
@@ -480,6 +481,12 @@ struct pr_index {
     int32_t n_rows, n_sub;
     int64_t heavy_min_df;
     bool lazy_ok;
+    // hot posting stream of the flat-step kernel (bm25_hot.cuh), also in the aux buffer
+    const int32_t *hot_of_row;
+    const uint32_t *hot_off;
+    const unsigned char *hot_stream;
+    int32_t n_hot;
+    int64_t hot_min_df, hot_stream_bytes;
 };
 
 namespace {
@@ -564,6 +571,21 @@ warp_fn_t pick_warp_fn(int nw, int E, bool lazy)
     return pick_warp<8, false>(E);
 }
 
+template <int NW>
+warp_fn_t pick_flat(int E)
+{
+    if (E == 1) return prf::bm25_flat_kernel<NW, 1>;
+    if (E == 2) return prf::bm25_flat_kernel<NW, 2>;
+    return prf::bm25_flat_kernel<NW, 4>;
+}
+
+warp_fn_t pick_flat_fn(int nw, int E)
+{
+    if (nw == 4) return pick_flat<4>(E);
+    if (nw == 12) return pick_flat<12>(E);
+    return pick_flat<8>(E);
+}
+
 int launch_merge(int E, dim3 grid, cudaStream_t st, const float *ps, const int32_t *pd, int C,
                  int64_t sq, int64_t sc, float *rs, int32_t *rd, float *rt, int B, int K, int fin,
                  float *os, int32_t *od, int base, int n_docs)
@@ -600,12 +622,15 @@ int check_tuning(const pr_bm25_tuning_t &t)
         return PR_EINVAL;
     }
     if (t.subs_per_item < 1 || t.docs_per_launch < 1 ||
-        (t.warps_per_cta != 4 && t.warps_per_cta != 8 && t.warps_per_cta != 9 && t.warps_per_cta != 13 && t.warps_per_cta != 16)) {
-        pr_set_error("bad tuning (subs_per_item=%d docs_per_launch=%d warps_per_cta=%d; warps_per_cta is 4, 8, 9, 13 or 16)",
+        (t.warps_per_cta != 4 && t.warps_per_cta != 8 && t.warps_per_cta != 9 && t.warps_per_cta != 12 &&
+         t.warps_per_cta != 13 && t.warps_per_cta != 16) ||
+        (t.mode >= 5 && t.warps_per_cta != 4 && t.warps_per_cta != 8 && t.warps_per_cta != 12)) {
+        pr_set_error("bad tuning (subs_per_item=%d docs_per_launch=%d warps_per_cta=%d; warps_per_cta is 4, 8, 9, 12, 13 or 16; "
+                     "4, 8 or 12 for modes 5/6)",
                      t.subs_per_item, t.docs_per_launch, t.warps_per_cta);
         return PR_EINVAL;
     }
-    if (t.tiles_per_item < 1 || t.mode < 1 || t.mode > 4 || t.min_items < 1 || t.cand_cap < 32) {
+    if (t.tiles_per_item < 1 || t.mode < 1 || t.mode > 6 || t.min_items < 1 || t.cand_cap < 32) {
         pr_set_error("bad tuning (tiles_per_item=%d mode=%d min_items=%d cand_cap=%d)",
                      t.tiles_per_item, t.mode, t.min_items, t.cand_cap);
         return PR_EINVAL;
@@ -679,6 +704,12 @@ extern "C" int pr_index_create(pr_index_t **out, int device, int64_t n_docs_glob
     ix->n_rows = 0;
     ix->n_sub = (int32_t)(((int64_t)n_docs + prw::kSub - 1) >> prw::kSubShift);
     ix->heavy_min_df = 0;
+    ix->hot_of_row = nullptr;
+    ix->hot_off = nullptr;
+    ix->hot_stream = nullptr;
+    ix->n_hot = 0;
+    ix->hot_min_df = 0;
+    ix->hot_stream_bytes = 0;
     {   // lazily re-zeroed accumulators need every weight in [2^-30, 2^10] (bm25_warp.cuh)
         float wmin, wmax;
         memcpy(&wmin, &h_bad3[1], 4);
@@ -727,7 +758,10 @@ extern "C" int pr_index_build_aux(pr_index_t *index, void *aux_dev, size_t aux_b
         pr_set_error("pr_index_build_aux: aux buffer of %zu bytes, need at least %zu", aux_bytes, o);
         return PR_EWORKSPACE;
     }
-    const size_t table_bytes = aux_bytes - o;
+    // the boundary table gets a fifth of the table budget (at least 16 MB of it), the hot stream the rest
+    const size_t budget = aux_bytes - o;
+    size_t table_bytes = budget / 5;
+    if (table_bytes < ((size_t)16 << 20)) table_bytes = budget < ((size_t)16 << 20) ? budget : ((size_t)16 << 20);
     const size_t per_row = ((size_t)index->n_sub + 1) * 4 + 4;   // tp row + row_term entry
     // smallest df threshold (doubling from kLightDf) whose table fits the budget
     int64_t min_df = prw::kLightDf;
@@ -742,7 +776,7 @@ extern "C" int pr_index_build_aux(pr_index_t *index, void *aux_dev, size_t aux_b
         min_df *= 2;
     }
     int32_t *row_term = (int32_t *)(p + o);   o = align_up(o + (size_t)(rows > 0 ? rows : 1) * 4, 256);
-    uint32_t *tp = (uint32_t *)(p + o);
+    uint32_t *tp = (uint32_t *)(p + o);       o = align_up(o + (size_t)rows * ((size_t)index->n_sub + 1) * 4, 256);
     if (nt > 0) {
         prw::heavy_block_count_kernel<<<n_blocks, 1024, 0, st>>>(index->indptr, nt, min_df, block_cnt);
         prw::heavy_block_scan_kernel<<<1, 32, 0, st>>>(block_cnt, n_blocks);
@@ -756,6 +790,70 @@ extern "C" int pr_index_build_aux(pr_index_t *index, void *aux_dev, size_t aux_b
     index->tp = tp;
     index->n_rows = rows;
     index->heavy_min_df = min_df;
+    index->hot_of_row = nullptr;
+    index->hot_off = nullptr;
+    index->hot_stream = nullptr;
+    index->n_hot = 0;
+    index->hot_min_df = 0;
+    index->hot_stream_bytes = 0;
+
+    // ---- hot posting stream (bm25_hot.cuh) for the tabulated terms with >= kHotMinSeg postings
+    // per sub-tile, as many of them as the rest of the buffer holds (threshold doubles until it fits)
+    const int n_sub = index->n_sub;
+    size_t oh = o;
+    int32_t *hot_of_row = (int32_t *)(p + oh);  oh = align_up(oh + (size_t)(rows > 0 ? rows : 1) * 4, 256);
+    int32_t *hot_rows = (int32_t *)(p + oh);    oh = align_up(oh + (size_t)(rows > 0 ? rows : 1) * 4, 256);
+    int32_t *n_hot_dev = (int32_t *)(p + oh);
+    uint32_t *total_dev = (uint32_t *)(p + oh + 64);
+    oh += 256;
+    if (rows == 0 || n_sub == 0 || oh + 4096 > aux_bytes) return PR_OK;
+    int64_t hot_df = ((int64_t)prh::kHotMinSeg * index->n_docs + prw::kSub - 1) / prw::kSub;
+    if (hot_df < min_df + 1) hot_df = min_df + 1;   // hot rows are a subset of the tabulated rows (df > min_df)
+    for (;; hot_df *= 2) {
+        int32_t H = 0;
+        prh::hot_assign_kernel<<<1, 32, 0, st>>>(index->indptr, row_term, rows, hot_df, hot_of_row, hot_rows, n_hot_dev);
+        PR_CUDA_CHECK(cudaGetLastError());
+        PR_CUDA_CHECK(cudaMemcpyAsync(&H, n_hot_dev, 4, cudaMemcpyDeviceToHost, st));
+        PR_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (H == 0) return PR_OK;
+        const int64_t n_seg = (int64_t)H * n_sub;
+        const int64_t nb = (n_seg + prh::kScanChunk - 1) / prh::kScanChunk;
+        size_t os = oh;
+        uint32_t *hot_off = (uint32_t *)(p + os);    os = align_up(os + (size_t)H * ((size_t)n_sub + 1) * 4, 256);
+        uint32_t *block_sum = (uint32_t *)(p + os);  os = align_up(os + (size_t)nb * 4, 256);
+        if (os > aux_bytes || nb > 0x7fffffff) continue;
+        uint32_t total = 0;
+        prh::hot_units_kernel<<<(unsigned)nb, 256, 0, st>>>(tp, hot_rows, n_sub, n_seg, block_sum);
+        prh::hot_block_scan_kernel<<<1, 32, 0, st>>>(block_sum, (int)nb, total_dev);
+        PR_CUDA_CHECK(cudaGetLastError());
+        PR_CUDA_CHECK(cudaMemcpyAsync(&total, total_dev, 4, cudaMemcpyDeviceToHost, st));
+        PR_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (os + (size_t)total * prh::kUnitBytes > aux_bytes) continue;
+        unsigned char *stream_dev = p + os;
+        prh::hot_offsets_kernel<<<(unsigned)nb, 256, 0, st>>>(tp, hot_rows, n_sub, n_seg, block_sum, hot_off);
+        prh::hot_fill_kernel<<<2368, 256, 0, st>>>(index->indptr, index->doc_ids, index->weights, row_term, tp, hot_rows, n_sub,
+                                                  n_seg, hot_off, stream_dev);
+        PR_CUDA_CHECK(cudaGetLastError());
+        PR_CUDA_CHECK(cudaStreamSynchronize(st));
+        index->hot_of_row = hot_of_row;
+        index->hot_off = hot_off;
+        index->hot_stream = stream_dev;
+        index->n_hot = H;
+        index->hot_min_df = hot_df;
+        index->hot_stream_bytes = (int64_t)total * prh::kUnitBytes;
+        return PR_OK;
+    }
+}
+
+extern "C" int pr_index_hot_info(const pr_index_t *index, int32_t *n_hot, int64_t *min_df, int64_t *stream_bytes)
+{
+    if (!index || !n_hot || !min_df || !stream_bytes) {
+        pr_set_error("pr_index_hot_info: null argument");
+        return PR_EINVAL;
+    }
+    *n_hot = index->n_hot;
+    *min_df = index->hot_min_df;
+    *stream_bytes = index->hot_stream_bytes;
     return PR_OK;
 }
 
@@ -891,12 +989,14 @@ extern "C" int pr_bm25_topk(pr_index_t *index, int32_t n_queries, const int64_t 
     }
     const int nw = warp_mode ? t.warps_per_cta : t.threads / 32;
     const int threads = nw * 32;
-    const size_t smem = warp_mode ? prw::warp_smem_bytes(nw) : score_smem_bytes(t.tile_docs, t.cand_cap, nw, k);
+    const bool flat_mode = t.mode >= 5;
+    const size_t smem = flat_mode ? prf::flat_smem_bytes(nw)
+                                  : warp_mode ? prw::warp_smem_bytes(nw) : score_smem_bytes(t.tile_docs, t.cand_cap, nw, k);
     score_fn_t fn = nullptr;
     warp_fn_t wfn = nullptr;
     const void *kfn = nullptr;
     if (warp_mode) {
-        wfn = pick_warp_fn(nw, E, index->lazy_ok && t.lazy_zero == 1);
+        wfn = flat_mode ? pick_flat_fn(nw, E) : pick_warp_fn(nw, E, index->lazy_ok && t.lazy_zero == 1);
         kfn = (const void *)wfn;
     } else {
         fn = pick_score_fn(t.threads, E);
@@ -938,6 +1038,9 @@ extern "C" int pr_bm25_topk(pr_index_t *index, int32_t n_queries, const int64_t 
     w.weights = index->weights;
     w.heavy_row = index->heavy_row;
     w.tp = index->tp;
+    w.hot_of_row = index->hot_of_row;
+    w.hot_off = index->hot_off;
+    w.hot_stream = index->hot_stream;
     w.q_indptr = q_indptr_dev;
     w.q_terms = q_terms_dev;
     w.run_theta = theta;
@@ -975,7 +1078,7 @@ extern "C" int pr_bm25_topk(pr_index_t *index, int32_t n_queries, const int64_t 
             w.chunk0 = li * l.C;
             w.n_chunks_launch = Cl;
             w.counter = counters + li;
-            w.mode = li == 0 ? 3 : t.mode;  // the first launch has no running k-th score yet
+            w.mode = li == 0 ? (flat_mode ? 5 : 3) : t.mode;  // the first launch has no running k-th score yet
             wfn<<<(unsigned)grid, threads, smem, st>>>(w);
         } else {
             a.chunk0 = li * l.C;

@@ -1,0 +1,209 @@
+// Hot posting stream: a private, kernel-friendly copy of the posting lists of the frequent terms.
+//
+// ncu on the scoring kernels (profiles/r01) shows the scatter into the shared-memory score tile
+// as the real bound: ~0.44 shared-memory wavefronts per posting (3.5-way bank conflicts on
+// random document offsets) and ~2 warp instructions per posting, most of them masks, offset
+// arithmetic and per-segment control for lists that hold a handful of postings per 2048-document
+// sub-tile.  99% of the postings a Zipf query batch touches belong to the few thousand terms
+// with >= 8 postings per sub-tile, so for those terms the index keeps, next to the CSR, every
+// (term, sub-tile) segment re-laid-out as a sequence of mask-free STEPS:
+//
+//   wide step   1 KB : [32 lanes x 4 tile byte-offsets u32][32 lanes x 4 weights f32]
+//   narrow step 256 B: [32 lanes x 1 tile byte-offset u32 ][32 lanes x 1 weight f32 ]
+//
+//   * offsets are pre-scaled byte offsets into the warp's tile (no masking / shifting per slot);
+//   * segments are padded to whole steps with (dummy word, +0.0f) slots, so there are no
+//     validity masks and no alignment heads;
+//   * inside a segment the postings are dealt round-robin over the steps' 32-slot groups in
+//     bank-sorted order (doc % 32), so the 32 documents a warp touches together fall into
+//     distinct banks whenever the segment's bank histogram allows it.
+//
+// The order of a term's postings inside a sub-tile is irrelevant for the sums (a document occurs
+// once per term), so scores stay bit-identical.  Everything is built on the device by
+// pr_index_build_aux into caller-owned memory.
+#pragma once
+
+#include "bm25_warp.cuh"
+
+namespace prh {
+
+using prw::kSub;
+using prw::kSubShift;
+
+constexpr int kHotMinSeg = 8;    // a term is hot when it averages >= 8 postings per sub-tile
+constexpr int kUnitBytes = 256;  // narrow step; a wide step is 4 units
+
+// 256-byte units a segment of n postings occupies: full wide steps, then the rest as narrow
+// steps (or one more wide step when the rest is > 96)
+__host__ __device__ __forceinline__ int seg_units(int n)
+{
+    int w = n >> 7, r = n & 127;
+    if (r > 96) {
+        ++w;
+        r = 0;
+    }
+    return 4 * w + ((r + 31) >> 5);
+}
+
+// hot_of_row[r] = exclusive rank of row r among the rows with df >= min_df, or -1; one warp.
+__global__ void hot_assign_kernel(const int64_t *indptr, const int32_t *row_term, int n_rows, int64_t min_df,
+                                  int32_t *hot_of_row, int32_t *hot_rows, int32_t *n_hot)
+{
+    const int lane = threadIdx.x & 31;
+    int acc = 0;
+    for (int r0 = 0; r0 < n_rows; r0 += 32) {
+        const int r = r0 + lane;
+        bool f = false;
+        if (r < n_rows) {
+            const int t = row_term[r];
+            f = (indptr[t + 1] - indptr[t]) >= min_df;
+        }
+        const unsigned m = __ballot_sync(PR_FULL_MASK, f);
+        const int h = acc + __popc(m & ((1u << lane) - 1u));
+        if (r < n_rows) {
+            hot_of_row[r] = f ? h : -1;
+            if (f && hot_rows) hot_rows[h] = r;
+        }
+        acc += __popc(m);
+    }
+    if (lane == 0) *n_hot = acc;
+}
+
+__device__ __forceinline__ int hot_seg_len(const uint32_t *tp, const int32_t *hot_rows, int n_sub, int64_t s)
+{
+    const int h = (int)(s / n_sub), g = (int)(s % n_sub);
+    const uint32_t *r = tp + (size_t)hot_rows[h] * ((size_t)n_sub + 1) + g;
+    return (int)(r[1] - r[0]);
+}
+
+constexpr int kScanChunk = 2048;  // segments per block of the offset scan (256 threads x 8)
+
+// block sums of seg_units over chunks of the flat (hot row, sub-tile) segment array
+__global__ void __launch_bounds__(256) hot_units_kernel(const uint32_t *tp, const int32_t *hot_rows, int n_sub, int64_t n_seg,
+                                                        uint32_t *block_sum)
+{
+    __shared__ uint32_t ws[8];
+    const int64_t s0 = (int64_t)blockIdx.x * kScanChunk + threadIdx.x * 8;
+    uint32_t local = 0;
+    for (int i = 0; i < 8; ++i)
+        if (s0 + i < n_seg) local += (uint32_t)seg_units(hot_seg_len(tp, hot_rows, n_sub, s0 + i));
+    for (int o = 16; o; o >>= 1) local += __shfl_down_sync(PR_FULL_MASK, local, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < 8; ++i) t += ws[i];
+        block_sum[blockIdx.x] = t;
+    }
+}
+
+__global__ void hot_block_scan_kernel(uint32_t *block_sum, int n_blocks, uint32_t *total)  // one thread: a few thousand blocks
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int i = 0; i < n_blocks; ++i) {
+            const uint32_t v = block_sum[i];
+            block_sum[i] = acc;
+            acc += v;
+        }
+        *total = acc;
+    }
+}
+
+// hot_off[h][g] = units before segment (h, g); hot_off[h][n_sub] = units before row h+1
+__global__ void __launch_bounds__(256) hot_offsets_kernel(const uint32_t *tp, const int32_t *hot_rows, int n_sub, int64_t n_seg,
+                                                          const uint32_t *block_off, uint32_t *hot_off)
+{
+    __shared__ uint32_t ws[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t s0 = (int64_t)blockIdx.x * kScanChunk + threadIdx.x * 8;
+    uint32_t u[8], local = 0;
+    for (int i = 0; i < 8; ++i) {
+        u[i] = s0 + i < n_seg ? (uint32_t)seg_units(hot_seg_len(tp, hot_rows, n_sub, s0 + i)) : 0u;
+        local += u[i];
+    }
+    uint32_t incl = local;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(PR_FULL_MASK, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) ws[w] = incl;
+    __syncthreads();
+    uint32_t pre = block_off[blockIdx.x] + incl - local;
+    for (int i = 0; i < w; ++i) pre += ws[i];
+    for (int i = 0; i < 8; ++i) {
+        const int64_t s = s0 + i;
+        if (s < n_seg) {
+            const int64_t h = s / n_sub;
+            const int g = (int)(s % n_sub);
+            hot_off[h * ((int64_t)n_sub + 1) + g] = pre;
+            if (g == n_sub - 1) hot_off[h * ((int64_t)n_sub + 1) + n_sub] = pre + u[i];
+        }
+        pre += u[i];
+    }
+}
+
+// one warp per (hot row, sub-tile) segment: pads, then the bank-aware deal of the postings
+__global__ void __launch_bounds__(256) hot_fill_kernel(const int64_t *indptr, const int32_t *doc_ids, const float *weights,
+                                                       const int32_t *row_term, const uint32_t *tp, const int32_t *hot_rows,
+                                                       int n_sub, int64_t n_seg, const uint32_t *hot_off, unsigned char *stream)
+{
+    __shared__ int s_fill[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int *fill = s_fill[w];
+    const int64_t n_warps = (int64_t)gridDim.x * 8;
+    for (int64_t s = (int64_t)blockIdx.x * 8 + w; s < n_seg; s += n_warps) {
+        const int h = (int)(s / n_sub), g = (int)(s % n_sub);
+        const int row = hot_rows[h];
+        const uint32_t *r = tp + (size_t)row * ((size_t)n_sub + 1) + g;
+        const int sb = (int)r[0], n = (int)(r[1] - r[0]);
+        if (n == 0) continue;
+        const int units = seg_units(n);
+        const int n_wide = units >> 2, n_narrow = units & 3, groups = 4 * n_wide + n_narrow;
+        uint32_t *out = reinterpret_cast<uint32_t *>(stream + (size_t)hot_off[(size_t)h * ((size_t)n_sub + 1) + g] * kUnitBytes);
+        // ---- padding pattern: the lane's dummy word behind the tile, weight +0.0f
+        for (int i = lane; i < n_wide * 256; i += 32) {
+            const int in_step = i & 255;
+            out[i] = in_step < 128 ? (uint32_t)(kSub + (in_step >> 2)) * 4u : 0u;
+        }
+        for (int i = lane; i < n_narrow * 64; i += 32) {
+            const int in_step = i & 63;
+            out[n_wide * 256 + i] = in_step < 32 ? (uint32_t)(kSub + in_step) * 4u : 0u;
+        }
+        // ---- bank histogram -> start of every bank in bank-sorted order
+        const int64_t p0 = indptr[row_term[row]] + sb;
+        fill[lane] = 0;
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) atomicAdd(&fill[doc_ids[p0 + i] & 31], 1);
+        __syncwarp();
+        const int c = fill[lane];
+        int incl = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(PR_FULL_MASK, incl, o);
+            if (lane >= o) incl += v;
+        }
+        __syncwarp();
+        fill[lane] = incl - c;
+        __syncwarp();
+        // ---- deal: the i-th posting in bank order goes to group i % groups, lane i / groups
+        for (int i = lane; i < n; i += 32) {
+            const int d = doc_ids[p0 + i];
+            const float wt = weights[p0 + i];
+            const int rank = atomicAdd(&fill[d & 31], 1);
+            const int grp = rank % groups, ln = rank / groups;
+            int ow, ww;
+            if (grp < 4 * n_wide) {
+                ow = (grp >> 2) * 256 + ln * 4 + (grp & 3);
+                ww = ow + 128;
+            } else {
+                ow = n_wide * 256 + (grp - 4 * n_wide) * 64 + ln;
+                ww = ow + 32;
+            }
+            out[ow] = (uint32_t)(d & (kSub - 1)) * 4u;
+            out[ww] = __float_as_uint(wt);
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace prh

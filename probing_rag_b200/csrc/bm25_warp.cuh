@@ -42,6 +42,9 @@ struct WarpArgs {
     const float *__restrict__ weights;
     const int32_t *__restrict__ heavy_row;  // [n_terms] row of `tp`, or -1
     const uint32_t *__restrict__ tp;        // [n_rows][n_sub+1] postings with doc < s*kSub
+    const int32_t *__restrict__ hot_of_row; // [n_rows] row of `hot_off`, or -1 (null: no hot stream)
+    const uint32_t *__restrict__ hot_off;   // [n_hot][n_sub+1] 256-byte units of the hot stream before (row, sub-tile)
+    const unsigned char *__restrict__ hot_stream;
     const int64_t *__restrict__ q_indptr;
     const int32_t *__restrict__ q_terms;
     const float *__restrict__ run_theta;

@@ -115,10 +115,11 @@ class BM25Index:
                 ctypes.byref(self._handle), self.device.index or 0, self.n_docs_global, self.doc_id_base,
                 self.n_docs, self.n_terms, self.nnz, self.indptr.data_ptr(),
                 self.doc_ids.data_ptr() if self.nnz else None, self.weights.data_ptr() if self.nnz else None))
-            # tables of the warp-autonomous kernel: posting offsets at every 2048-doc boundary
-            # for the frequent terms, within ~1/4 of the index size (min 16 MB, max 8 GB)
+            # per-index structures of the scoring kernel: posting offsets at every 2048-doc boundary
+            # for the frequent terms (a fifth of the budget) and the hot posting stream (the rest);
+            # 12 bytes per posting by default (min 64 MB, max 48 GB)
             budget = aux_budget_bytes if aux_budget_bytes is not None else \
-                int(min(max(self.nnz * 2, 16 << 20), 8 << 30))
+                int(min(max(self.nnz * 12, 64 << 20), 48 << 30))
             nbytes = int(L.pr_index_aux_bytes(self._handle, budget))
             self._aux = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             _lib.check(L.pr_index_build_aux(self._handle, self._aux.data_ptr(), nbytes,
@@ -206,7 +207,11 @@ class BM25Index:
     def aux_info(self) -> dict:
         rows, min_df = ctypes.c_int32(), ctypes.c_int64()
         _lib.check(_lib.lib().pr_index_aux_info(self._handle, ctypes.byref(rows), ctypes.byref(min_df)))
-        return {"tp_rows": int(rows.value), "tp_min_df": int(min_df.value), "aux_bytes": int(self._aux.numel())}
+        n_hot, hot_df, hot_bytes = ctypes.c_int32(), ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(_lib.lib().pr_index_hot_info(self._handle, ctypes.byref(n_hot), ctypes.byref(hot_df),
+                                                 ctypes.byref(hot_bytes)))
+        return {"tp_rows": int(rows.value), "tp_min_df": int(min_df.value), "aux_bytes": int(self._aux.numel()),
+                "hot_rows": int(n_hot.value), "hot_min_df": int(hot_df.value), "hot_stream_bytes": int(hot_bytes.value)}
 
     @property
     def last_launches(self) -> int:

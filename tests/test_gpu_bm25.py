@@ -29,6 +29,10 @@ TUNINGS = [
     dict(mode=3, subs_per_item=7, warps_per_cta=9, docs_per_launch=98304, lazy_zero=2),
     dict(mode=4, subs_per_item=1, warps_per_cta=4, docs_per_launch=2048, min_items=1),      # one sub-tile per item, many launches
     dict(mode=4, subs_per_item=5, warps_per_cta=16, docs_per_launch=1000000, min_items=100000),  # one launch
+    dict(mode=6, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304),                  # flat-step kernel
+    dict(mode=5, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304),
+    dict(mode=6, subs_per_item=1, warps_per_cta=4, docs_per_launch=2048, min_items=1),
+    dict(mode=6, subs_per_item=5, warps_per_cta=12, docs_per_launch=1000000, min_items=100000),
     dict(threads=512, tile_docs=2048, tiles_per_item=1, mode=2, min_items=1),   # many launches
     dict(threads=512, tile_docs=16384, tiles_per_item=2, mode=1, min_items=100000),  # one launch
 ]
@@ -85,7 +89,9 @@ def test_depth_sweep(small_corpus, corpus_gpu, k):
     os_, od = co.retrieve_batch(small_corpus["index"], qi, qt, k, n_threads=8)
     for tun in (dict(threads=512, tile_docs=24576, tiles_per_item=4, mode=2, min_items=2048, cand_cap=1024),
                 dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
-                dict(mode=3, subs_per_item=3, warps_per_cta=8, docs_per_launch=20000, min_items=2048)):
+                dict(mode=3, subs_per_item=3, warps_per_cta=8, docs_per_launch=20000, min_items=2048),
+                dict(mode=6, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
+                dict(mode=5, subs_per_item=3, warps_per_cta=12, docs_per_launch=20000, min_items=2048)):
         corpus_gpu.set_tuning(**tun)
         gs, gd = run_gpu(corpus_gpu, qi, qt, k)
         assert_parity(gs, gd, os_, od)
@@ -97,7 +103,8 @@ def test_small_batches(small_corpus, corpus_gpu, nq):
     qi, qt = small_corpus["q_indptr"][:nq + 1], small_corpus["q_terms"]
     os_, od = co.retrieve_batch(small_corpus["index"], qi, qt, 10)
     for tun in (dict(threads=512, tile_docs=24576, tiles_per_item=4, mode=2, min_items=2048, cand_cap=1024),
-                dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048)):
+                dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
+                dict(mode=6, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048)):
         corpus_gpu.set_tuning(**tun)
         gs, gd = run_gpu(corpus_gpu, qi, qt, 10)
         assert_parity(gs, gd, os_, od)
@@ -110,7 +117,7 @@ def test_long_transcript_queries(small_corpus, corpus_gpu):
     qi, qt = synth.queries_np(48, small_corpus["vocab"], idx["df"], kind="later")
     assert np.diff(qi).max() > 256
     os_, od = co.retrieve_batch(idx, qi, qt, 10, n_threads=8)
-    for mode in (1, 2, 3, 4):
+    for mode in (1, 2, 3, 4, 5, 6):
         corpus_gpu.set_tuning(threads=512, tile_docs=24576, tiles_per_item=2, mode=mode, min_items=2048,
                               subs_per_item=4, warps_per_cta=8, docs_per_launch=98304)
         gs, gd = run_gpu(corpus_gpu, qi, qt, 10)
@@ -130,7 +137,7 @@ def test_edge_queries(small_corpus, corpus_gpu):
     qi[1:] = np.cumsum([len(q) for q in queries])
     qt = np.array([t for q in queries for t in q], dtype=np.int32)
     os_, od = bo.retrieve_batch(idx, qi, qt, 10)
-    for tun in TUNINGS[:3] + TUNINGS[4:10]:
+    for tun in TUNINGS[:3] + TUNINGS[4:14]:
         corpus_gpu.set_tuning(**tun)
         gs, gd = run_gpu(corpus_gpu, qi, qt, 10)
         assert_parity(gs, gd, os_, od)
@@ -184,10 +191,32 @@ def test_tie_heavy_corpus():
                     dict(mode=4, subs_per_item=2, warps_per_cta=4, docs_per_launch=4096, min_items=1),
                     dict(mode=3, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=100000),
                     dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
-                    dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048, lazy_zero=2)):
+                    dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048, lazy_zero=2),
+                    dict(mode=6, subs_per_item=2, warps_per_cta=4, docs_per_launch=4096, min_items=1),
+                    dict(mode=5, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=100000),
+                    dict(mode=6, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048)):
             gi.set_tuning(**dict(dict(lazy_zero=1), **tun))
             gs, gd = run_gpu(gi, qi, qt, k)
             assert_parity(gs, gd, os_, od)
+
+
+@pytest.mark.parametrize("mode", [4, 6])
+def test_without_boundary_tables_every_term_takes_the_cursor_path(small_corpus, mode):
+    """aux budget 0 -> no term is tabulated: the head terms (thousands of postings per sub-tile,
+    clustered far beyond the lane-local scan limit) go through the rare-term cursor + warp search."""
+    gi = gpu_index(small_corpus["index"], aux_budget_bytes=0)
+    assert gi.aux_info()["tp_rows"] == 0
+    qi, qt = small_corpus["q_indptr"][:201], small_corpus["q_terms"]
+    os_, od = co.retrieve_batch(small_corpus["index"], qi, qt, 10, n_threads=8)
+    for tun in (dict(mode=mode, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304),
+                dict(mode=mode, subs_per_item=3, warps_per_cta=4, docs_per_launch=8192, min_items=1)):
+        gi.set_tuning(**tun)
+        gs, gd = run_gpu(gi, qi, qt, 10)
+        assert_parity(gs, gd, os_, od)
+    lq, lt = synth.queries_np(8, small_corpus["vocab"], small_corpus["index"]["df"], kind="later")
+    os_, od = co.retrieve_batch(small_corpus["index"], lq, lt, 10, n_threads=8)
+    gs, gd = run_gpu(gi, lq, lt, 10)
+    assert_parity(gs, gd, os_, od)
 
 
 def test_doc_range_shards_and_merge_equal_single_index(small_corpus, corpus_gpu):

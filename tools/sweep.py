@@ -32,6 +32,7 @@ def main():
     gi, qi, qt = bench.build_workload(args.n_docs, args.vocab, args.n_queries, dev)
     d_qi, d_qt = torch.from_numpy(qi).to(dev), torch.from_numpy(qt).to(dev)
     alg = gi.algorithmic_bytes(qi, qt, args.k)
+    print(json.dumps({"aux": gi.aux_info()}), flush=True)
     if args.configs:
         cfgs = [{kv.split("=")[0]: int(kv.split("=")[1]) for kv in c.split(",")} for c in args.configs.split(";")]
     elif args.grid == "warp":

@@ -47,7 +47,8 @@ typedef struct pr_bm25_tuning {
     int32_t threads;        /* 256, 512 or 1024                                               */
     int32_t mode;           /* CTA-cooperative kernel: 1 = scan select, 2 = threshold-on-update; warp-autonomous
                                segment-loop kernel: 3 = scan select, 4 = threshold-on-update; warp-autonomous
-                               flat-step kernel: 5 = scan select, 6 = threshold-on-update        */
+                               flat-step kernel: 5 = scan select, 6 = threshold-on-update, 7 = 6 + rank-safe
+                               skipping of frequent terms with exact rescoring of the candidates */
     int32_t min_items;      /* doc ranges are split until a launch has this many work items   */
     int32_t cand_cap;       /* candidate buffer entries per CTA (mode 2)                      */
     /* warp-autonomous kernel (modes 3 = scan select, 4 = threshold-on-update select) */
@@ -55,6 +56,7 @@ typedef struct pr_bm25_tuning {
     int32_t warps_per_cta;  /* 4, 8, 9, 12, 13 or 16 (modes 5/6: 4, 8 or 12)                    */
     int32_t docs_per_launch;/* document range one launch covers for large batches (L2 reuse)   */
     int32_t lazy_zero;      /* 1 = epoch-tagged accumulators, re-zeroed every 7th sub-tile; 2 = off */
+    int32_t rescore_cost;   /* mode 7 planner: cost of rescoring one candidate, in postings (default 64) */
 } pr_bm25_tuning_t;
 
 int pr_version(void);

@@ -22,7 +22,7 @@ class Tuning(ctypes.Structure):
     _fields_ = [("tile_docs", c_i32), ("tiles_per_item", c_i32), ("threads", c_i32),
                 ("mode", c_i32), ("min_items", c_i32), ("cand_cap", c_i32),
                 ("subs_per_item", c_i32), ("warps_per_cta", c_i32), ("docs_per_launch", c_i32),
-                ("lazy_zero", c_i32)]
+                ("lazy_zero", c_i32), ("rescore_cost", c_i32)]
 
 
 class ProberSet(ctypes.Structure):

@@ -400,15 +400,20 @@ __global__ void __launch_bounds__(128) bm25_merge_kernel(
     }
 }
 
-__global__ void bm25_init_kernel(float *run_s, int32_t *run_d, float *run_theta, int64_t n_run,
-                                 int B, int32_t *counters, int n_counters, int32_t *status)
+__global__ void bm25_init_kernel(float *run_s, int32_t *run_d, float *run_theta, float *plan_theta, uint32_t *plan_mask,
+                                 float *plan_m, int64_t n_run, int B, int32_t *counters, int n_counters, int32_t *status)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_run) {
         run_s[i] = PR_SENT_SCORE;
         run_d[i] = PR_SENT_DOC;
     }
-    if (i < B) run_theta[i] = PR_SENT_SCORE;
+    if (i < B) {
+        run_theta[i] = PR_SENT_SCORE;
+        plan_theta[i] = -2.f;   // no plan yet (mode 7)
+        plan_mask[i] = 0u;
+        plan_m[i] = 0.f;
+    }
     if (i < n_counters) counters[i] = 0;
     if (i == 0) *status = 0;
 }
@@ -487,13 +492,16 @@ struct pr_index {
     const unsigned char *hot_stream;
     int32_t n_hot;
     int64_t hot_min_df, hot_stream_bytes;
+    // largest weight per term (rank-safe term skipping, mode 7), also in the aux buffer
+    const float *term_maxw;
+    const float *row_q;   // [n_rows][2] weight levels ~1% / ~10% of a tabulated row's postings reach (planner cost model)
 };
 
 namespace {
 
 struct Layout {
     int n_chunks, C, L;
-    size_t off_status, off_counters, off_theta, off_run_s, off_run_d, off_part_s, off_part_d, total;
+    size_t off_status, off_counters, off_theta, off_plan_theta, off_plan_mask, off_plan_m, off_run_s, off_run_d, off_part_s, off_part_d, total;
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -520,6 +528,9 @@ Layout make_layout(const pr_index *ix, int32_t B, int32_t K)
     l.off_status = o;   o = align_up(o + 64, 256);
     l.off_counters = o; o = align_up(o + (size_t)(l.L + 1) * 4, 256);
     l.off_theta = o;    o = align_up(o + (size_t)B * 4, 256);
+    l.off_plan_theta = o; o = align_up(o + (size_t)B * 4, 256);
+    l.off_plan_mask = o;  o = align_up(o + (size_t)B * 4, 256);
+    l.off_plan_m = o;     o = align_up(o + (size_t)B * 4, 256);
     l.off_run_s = o;    o = align_up(o + (size_t)B * K * 4, 256);
     l.off_run_d = o;    o = align_up(o + (size_t)B * K * 4, 256);
     l.off_part_s = o;   o = align_up(o + (size_t)B * l.C * K * 4, 256);
@@ -571,19 +582,24 @@ warp_fn_t pick_warp_fn(int nw, int E, bool lazy)
     return pick_warp<8, false>(E);
 }
 
-template <int NW>
+template <int NW, bool SKIP>
 warp_fn_t pick_flat(int E)
 {
-    if (E == 1) return prf::bm25_flat_kernel<NW, 1>;
-    if (E == 2) return prf::bm25_flat_kernel<NW, 2>;
-    return prf::bm25_flat_kernel<NW, 4>;
+    if (E == 1) return prf::bm25_flat_kernel<NW, 1, SKIP>;
+    if (E == 2) return prf::bm25_flat_kernel<NW, 2, SKIP>;
+    return prf::bm25_flat_kernel<NW, 4, SKIP>;
 }
 
-warp_fn_t pick_flat_fn(int nw, int E)
+warp_fn_t pick_flat_fn(int nw, int E, bool skip)
 {
-    if (nw == 4) return pick_flat<4>(E);
-    if (nw == 12) return pick_flat<12>(E);
-    return pick_flat<8>(E);
+    if (skip) {
+        if (nw == 4) return pick_flat<4, true>(E);
+        if (nw == 12) return pick_flat<12, true>(E);
+        return pick_flat<8, true>(E);
+    }
+    if (nw == 4) return pick_flat<4, false>(E);
+    if (nw == 12) return pick_flat<12, false>(E);
+    return pick_flat<8, false>(E);
 }
 
 int launch_merge(int E, dim3 grid, cudaStream_t st, const float *ps, const int32_t *pd, int C,
@@ -609,6 +625,7 @@ void default_tuning(pr_bm25_tuning_t *t)
     t->warps_per_cta = 8;
     t->docs_per_launch = 98304;
     t->lazy_zero = 2;
+    t->rescore_cost = 64;
 }
 
 int check_tuning(const pr_bm25_tuning_t &t)
@@ -630,7 +647,7 @@ int check_tuning(const pr_bm25_tuning_t &t)
                      t.subs_per_item, t.docs_per_launch, t.warps_per_cta);
         return PR_EINVAL;
     }
-    if (t.tiles_per_item < 1 || t.mode < 1 || t.mode > 6 || t.min_items < 1 || t.cand_cap < 32) {
+    if (t.tiles_per_item < 1 || t.mode < 1 || t.mode > 7 || t.min_items < 1 || t.cand_cap < 32) {
         pr_set_error("bad tuning (tiles_per_item=%d mode=%d min_items=%d cand_cap=%d)",
                      t.tiles_per_item, t.mode, t.min_items, t.cand_cap);
         return PR_EINVAL;
@@ -710,6 +727,8 @@ extern "C" int pr_index_create(pr_index_t **out, int device, int64_t n_docs_glob
     ix->n_hot = 0;
     ix->hot_min_df = 0;
     ix->hot_stream_bytes = 0;
+    ix->term_maxw = nullptr;
+    ix->row_q = nullptr;
     {   // lazily re-zeroed accumulators need every weight in [2^-30, 2^10] (bm25_warp.cuh)
         float wmin, wmax;
         memcpy(&wmin, &h_bad3[1], 4);
@@ -736,7 +755,7 @@ extern "C" size_t pr_index_aux_bytes(const pr_index_t *index, size_t table_budge
 {
     if (!index) return 0;
     // heavy_row[n_terms] + block counts + row_term/tp within the budget
-    const size_t fixed = align_up((size_t)index->n_terms * 4, 256) + align_up(((size_t)index->n_terms / 1024 + 2) * 4, 256) + 256;
+    const size_t fixed = 2 * align_up((size_t)index->n_terms * 4, 256) + align_up(((size_t)index->n_terms / 1024 + 2) * 4, 256) + 256;
     return fixed + align_up(table_budget_bytes, 256);
 }
 
@@ -752,6 +771,7 @@ extern "C" int pr_index_build_aux(pr_index_t *index, void *aux_dev, size_t aux_b
     unsigned char *p = (unsigned char *)aux_dev;
     size_t o = 0;
     int32_t *heavy_row = (int32_t *)(p + o);  o = align_up(o + (size_t)nt * 4, 256);
+    float *term_maxw = (float *)(p + o);      o = align_up(o + (size_t)nt * 4, 256);
     int32_t *block_cnt = (int32_t *)(p + o);  o = align_up(o + ((size_t)nt / 1024 + 2) * 4, 256);
     int32_t *count = (int32_t *)(p + o);      o += 256;
     if (o > aux_bytes) {
@@ -762,7 +782,7 @@ extern "C" int pr_index_build_aux(pr_index_t *index, void *aux_dev, size_t aux_b
     const size_t budget = aux_bytes - o;
     size_t table_bytes = budget / 5;
     if (table_bytes < ((size_t)16 << 20)) table_bytes = budget < ((size_t)16 << 20) ? budget : ((size_t)16 << 20);
-    const size_t per_row = ((size_t)index->n_sub + 1) * 4 + 4;   // tp row + row_term entry
+    const size_t per_row = ((size_t)index->n_sub + 1) * 4 + 12;  // tp row + row_term entry + row_q pair
     // smallest df threshold (doubling from kLightDf) whose table fits the budget
     int64_t min_df = prw::kLightDf;
     int32_t rows = 0;
@@ -772,21 +792,28 @@ extern "C" int pr_index_build_aux(pr_index_t *index, void *aux_dev, size_t aux_b
         PR_CUDA_CHECK(cudaGetLastError());
         PR_CUDA_CHECK(cudaMemcpyAsync(&rows, count, 4, cudaMemcpyDeviceToHost, st));
         PR_CUDA_CHECK(cudaStreamSynchronize(st));
-        if ((size_t)rows * per_row + 512 <= table_bytes || rows == 0) break;
+        if ((size_t)rows * per_row + 1024 <= table_bytes || rows == 0) break;
         min_df *= 2;
     }
     int32_t *row_term = (int32_t *)(p + o);   o = align_up(o + (size_t)(rows > 0 ? rows : 1) * 4, 256);
+    float *row_q = (float *)(p + o);          o = align_up(o + (size_t)(rows > 0 ? rows : 1) * 8, 256);
     uint32_t *tp = (uint32_t *)(p + o);       o = align_up(o + (size_t)rows * ((size_t)index->n_sub + 1) * 4, 256);
     if (nt > 0) {
+        prw::term_maxw_kernel<<<2368, 256, 0, st>>>(index->indptr, index->weights, nt, term_maxw);
         prw::heavy_block_count_kernel<<<n_blocks, 1024, 0, st>>>(index->indptr, nt, min_df, block_cnt);
         prw::heavy_block_scan_kernel<<<1, 32, 0, st>>>(block_cnt, n_blocks);
         prw::heavy_assign_kernel<<<n_blocks, 1024, 0, st>>>(index->indptr, nt, min_df, block_cnt, heavy_row, row_term);
-        if (rows > 0)
+        if (rows > 0) {
             prw::tp_fill_kernel<<<2368, 256, 0, st>>>(index->indptr, index->doc_ids, row_term, rows, index->n_sub, tp);
+            prw::row_quantile_kernel<<<rows < 2368 ? rows : 2368, 256, 0, st>>>(index->indptr, index->weights, row_term, term_maxw,
+                                                                               rows, row_q);
+        }
     }
     PR_CUDA_CHECK(cudaGetLastError());
     PR_CUDA_CHECK(cudaStreamSynchronize(st));
     index->heavy_row = heavy_row;
+    index->term_maxw = term_maxw;
+    index->row_q = row_q;
     index->tp = tp;
     index->n_rows = rows;
     index->heavy_min_df = min_df;
@@ -914,6 +941,7 @@ extern "C" int pr_index_set_tuning(pr_index_t *index, const pr_bm25_tuning_t *tu
     if (tuning->warps_per_cta) t.warps_per_cta = tuning->warps_per_cta;
     if (tuning->docs_per_launch) t.docs_per_launch = tuning->docs_per_launch;
     if (tuning->lazy_zero) t.lazy_zero = tuning->lazy_zero;
+    if (tuning->rescore_cost) t.rescore_cost = tuning->rescore_cost;
     const int rc = check_tuning(t);
     if (rc != PR_OK) return rc;
     index->tuning = t;
@@ -970,6 +998,9 @@ extern "C" int pr_bm25_topk(pr_index_t *index, int32_t n_queries, const int64_t 
     int32_t *status = (int32_t *)(ws + l.off_status);
     int32_t *counters = (int32_t *)(ws + l.off_counters);
     float *theta = (float *)(ws + l.off_theta);
+    float *plan_theta = (float *)(ws + l.off_plan_theta);
+    uint32_t *plan_mask = (uint32_t *)(ws + l.off_plan_mask);
+    float *plan_m = (float *)(ws + l.off_plan_m);
     float *run_s = (float *)(ws + l.off_run_s);
     int32_t *run_d = (int32_t *)(ws + l.off_run_d);
     float *part_s = (float *)(ws + l.off_part_s);
@@ -977,8 +1008,9 @@ extern "C" int pr_bm25_topk(pr_index_t *index, int32_t n_queries, const int64_t 
 
     const int64_t n_run = (int64_t)n_queries * k;
     int64_t n_init = n_run > l.L + 1 ? n_run : l.L + 1;
-    bm25_init_kernel<<<(unsigned)((n_init + 255) / 256), 256, 0, st>>>(run_s, run_d, theta, n_run, n_queries,
-                                                                       counters, l.L + 1, status);
+    if (n_init < n_queries) n_init = n_queries;
+    bm25_init_kernel<<<(unsigned)((n_init + 255) / 256), 256, 0, st>>>(run_s, run_d, theta, plan_theta, plan_mask, plan_m, n_run,
+                                                                       n_queries, counters, l.L + 1, status);
     PR_CUDA_CHECK(cudaGetLastError());
     index->last_launches++;
 
@@ -996,7 +1028,7 @@ extern "C" int pr_bm25_topk(pr_index_t *index, int32_t n_queries, const int64_t 
     warp_fn_t wfn = nullptr;
     const void *kfn = nullptr;
     if (warp_mode) {
-        wfn = flat_mode ? pick_flat_fn(nw, E) : pick_warp_fn(nw, E, index->lazy_ok && t.lazy_zero == 1);
+        wfn = flat_mode ? pick_flat_fn(nw, E, t.mode == 7) : pick_warp_fn(nw, E, index->lazy_ok && t.lazy_zero == 1);
         kfn = (const void *)wfn;
     } else {
         fn = pick_score_fn(t.threads, E);
@@ -1041,6 +1073,9 @@ extern "C" int pr_bm25_topk(pr_index_t *index, int32_t n_queries, const int64_t 
     w.hot_of_row = index->hot_of_row;
     w.hot_off = index->hot_off;
     w.hot_stream = index->hot_stream;
+    w.term_maxw = index->term_maxw;
+    w.plan_mask = plan_mask;
+    w.plan_m = plan_m;
     w.q_indptr = q_indptr_dev;
     w.q_terms = q_terms_dev;
     w.run_theta = theta;
@@ -1074,6 +1109,9 @@ extern "C" int pr_bm25_topk(pr_index_t *index, int32_t n_queries, const int64_t 
             }
             PR_CUDA_CHECK(cudaEventRecord(index->ev[index->ev_used], st));
         }
+#ifdef PR_STATS
+        PR_CUDA_CHECK(cudaMemcpyToSymbolAsync(pr_stats_launch, &li, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+#endif
         if (warp_mode) {
             w.chunk0 = li * l.C;
             w.n_chunks_launch = Cl;
@@ -1097,9 +1135,28 @@ extern "C" int pr_bm25_topk(pr_index_t *index, int32_t n_queries, const int64_t 
                                     index->doc_id_base, index->n_docs);
         if (rc != PR_OK) return rc;
         index->last_launches += 2;
+        if (t.mode == 7 && li + 1 < l.L) {  // which terms the next launch may skip, given the new k-th scores
+            prf::bm25_plan_kernel<<<mgrid, 128, 0, st>>>(q_indptr_dev, q_terms_dev, index->indptr, index->heavy_row,
+                                                        index->term_maxw, index->row_q, theta, plan_theta, plan_mask, plan_m,
+                                                        n_queries, index->n_terms, (float)t.rescore_cost);
+            PR_CUDA_CHECK(cudaGetLastError());
+            index->last_launches++;
+        }
     }
     return PR_OK;
 }
+
+#ifdef PR_STATS
+// instrumented variant build only: copies the per-launch counters out and clears them
+extern "C" int pr_debug_stats(unsigned long long *out_host, int n)
+{
+    PR_CUDA_CHECK(cudaDeviceSynchronize());
+    PR_CUDA_CHECK(cudaMemcpyFromSymbol(out_host, pr_stats_dev, (size_t)n * 8));
+    static unsigned long long zeros[512 * 16];
+    PR_CUDA_CHECK(cudaMemcpyToSymbol(pr_stats_dev, zeros, sizeof(zeros)));
+    return PR_OK;
+}
+#endif
 
 extern "C" int pr_bm25_status(const void *workspace_dev, pr_stream_t stream)
 {

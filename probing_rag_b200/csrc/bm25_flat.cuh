@@ -18,6 +18,17 @@
 //     boundary table `tp`, rare terms through a per-lane cursor, so a term emits a step only for
 //     the sub-tiles where it really has postings.
 //
+//
+// Mode 7 adds RANK-SAFE TERM SKIPPING (MaxScore-style) on top of mode 6.  Once a query has a
+// running k-th score theta (from the launches before), the tabulated terms are sorted by the
+// largest weight of their list (term_maxw) and the longest prefix whose bounds add up to M < theta
+// is not accumulated at all: a document matching only skipped terms scores <= M < theta and can
+// never enter the top-k.  The tile then holds the partial sum `a(d)` of the remaining terms, the
+// push threshold becomes theta - M, and every pushed candidate is RESCORED exactly: each lane
+// binary-searches its term's segment for the document and the weights are added in query-token
+// order in fp32, so what enters the list is bit-identical to the exhaustive modes.  Safety
+// margins (1e-5 relative) cover the fp32 rounding of the partial sums (<= 32 terms).
+//
 // ncu history of this kernel is under profiles/r01 (v3 = segment-loop kernel it replaces).
 #pragma once
 
@@ -29,6 +40,14 @@
 #endif
 #ifndef PR_FLAT_CTAS
 #define PR_FLAT_CTAS 3
+#endif
+
+#ifdef PR_STATS  // instrumented variant build only (tools/skip_stats.py): per-launch event counters
+__device__ unsigned long long pr_stats_dev[512 * 16];
+__device__ int pr_stats_launch;
+#define PR_STAT(i, v) st_acc[i] += (v)
+#else
+#define PR_STAT(i, v)
 #endif
 
 namespace prf {
@@ -93,7 +112,133 @@ __device__ __forceinline__ float ldg_stream_f1(const void *p)
     return r;
 }
 
-template <int NW, int E>
+// Exact scores of up to 32/nq candidate documents of sub-tile g for a query of nq <= 32 terms.
+// Lane l serves (candidate l / nq, term l % nq): it looks the term's weight for the document up
+// (tabulated terms: binary search inside the sub-tile's segment; other terms: the whole list,
+// at most the table threshold long); then every lane adds its candidate's nq weights in
+// query-token order in fp32 (absent terms add +0.0f, which is exact), i.e. exactly what the
+// exhaustive modes accumulate.  `offs` = the candidates' tile offsets in shared memory, n of them
+// (n * nq <= 32).  Returns the score of candidate l / nq.  Warp-collective; rare, kept out of line.
+__device__ __noinline__ float flat_rescore(const int32_t *__restrict__ q_terms, int nq, const int64_t *__restrict__ indptr,
+                                           const int32_t *__restrict__ heavy_row, const uint32_t *__restrict__ tp,
+                                           const int32_t *__restrict__ doc_ids, const float *__restrict__ weights,
+                                           int n_terms, int n_sub, int g, const int32_t *offs, int n)
+{
+    const int lane = threadIdx.x & 31;
+    const int ci = lane / nq, tj = lane - ci * nq;
+    float w = 0.f;
+    if (ci < n) {
+        const int doc = (g << kSubShift) + offs[ci];
+        const int32_t t = q_terms[tj];
+        if (t >= 0 && t < n_terms) {
+            const int64_t b0 = indptr[t];
+            int64_t lo = 0, hi = indptr[t + 1] - b0;
+            const int row = heavy_row[t];
+            if (row >= 0) {
+                const uint32_t *r = tp + (size_t)row * ((size_t)n_sub + 1) + g;
+                lo = r[0];
+                hi = r[1];
+            }
+            const int64_t end = hi;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (__ldg(doc_ids + b0 + mid) < doc) lo = mid + 1;
+                else hi = mid;
+            }
+            if (lo < end && __ldg(doc_ids + b0 + lo) == doc) w = __ldg(weights + b0 + lo);
+        }
+    }
+    float s = 0.f;
+    const int base = min(ci, 31 / nq) * nq;  // idle lanes read a valid group
+    for (int j = 0; j < nq; ++j) s += __shfl_sync(PR_FULL_MASK, w, base + j);
+    return s;
+}
+
+// ---- mode-7 planner: which terms of a query to skip, given its running k-th score theta ------
+// One warp per query (nq <= 32, lane j <-> term j), run after every merge.  Only tabulated terms
+// can be skipped; they are taken in ascending (term_maxw, position) order and every prefix whose
+// bounds add up to M < theta (margins included) is a SAFE choice: a document matching only
+// skipped terms scores <= M < theta.  Among the safe prefixes the planner takes the cheapest
+// under a cost model in units of postings: the lists that stay cost df each, and every posting of
+// a remaining list that alone reaches the push threshold theta - M costs `rescore_cost` more
+// (fraction estimated from the list's max / 1% / 10% weight levels).  The choice only affects
+// speed: any safe prefix gives bit-identical results.
+__global__ void __launch_bounds__(128) bm25_plan_kernel(const int64_t *__restrict__ q_indptr, const int32_t *__restrict__ q_terms,
+                                                       const int64_t *__restrict__ indptr, const int32_t *__restrict__ heavy_row,
+                                                       const float *__restrict__ term_maxw, const float *__restrict__ row_q,
+                                                       const float *__restrict__ run_theta, float *plan_theta,
+                                                       uint32_t *plan_mask, float *plan_m, int B, int n_terms, float rescore_cost)
+{
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= B) return;
+    const float theta = run_theta[q];
+    if (theta == plan_theta[q]) return;  // unchanged since the last plan
+    const int64_t qb = q_indptr[q];
+    const int nq = (int)(q_indptr[q + 1] - qb);
+    uint32_t best_mask = 0;
+    float best_m = 0.f;
+    if (theta > 0.f && nq > 1 && nq <= 32) {
+        const float inf = __int_as_float(0x7f800000);
+        float df = 0.f, mw = 0.f, q99 = 0.f, q90 = 0.f, key = inf;
+        if (lane < nq) {
+            const int32_t t = q_terms[qb + lane];
+            if (t >= 0 && t < n_terms) {
+                df = (float)(indptr[t + 1] - indptr[t]);
+                mw = term_maxw[t];
+                q99 = q90 = mw;
+                const int row = heavy_row[t];
+                if (row >= 0) {
+                    key = mw;
+                    q99 = row_q[2 * row];
+                    q90 = row_q[2 * row + 1];
+                }
+            }
+        }
+        float sum_le = 0.f;  // bounds of the skippable terms ordered before or at this lane's
+        for (int i = 0; i < nq; ++i) {
+            const float ki = __shfl_sync(PR_FULL_MASK, key, i);
+            if (ki < key || (ki == key && i <= lane)) sum_le += ki;
+        }
+        const float lim = theta * 0.99998f;
+        const bool feasible = key < inf && sum_le * 1.00001f < lim;
+        // cost of skipping nothing: the exhaustive pass over every list
+        float c0 = df;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) c0 += __shfl_xor_sync(PR_FULL_MASK, c0, o);
+        float best_cost = c0;
+        unsigned fm = __ballot_sync(PR_FULL_MASK, feasible);
+        while (fm) {
+            const int i = __ffs(fm) - 1;  // candidate prefix: everything ordered before or at lane i
+            fm &= fm - 1;
+            const float ki = __shfl_sync(PR_FULL_MASK, key, i);
+            const float m = __shfl_sync(PR_FULL_MASK, sum_le, i) * 1.00001f;
+            const float push = lim - m;
+            const bool skipped = key < ki || (key == ki && lane <= i);
+            float c = 0.f;
+            if (!skipped && df > 0.f) {
+                const float frac = push > mw ? 0.f : push >= q99 ? 0.01f : push >= q90 ? 0.1f : 1.f;
+                c = df * (1.f + rescore_cost * frac);
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(PR_FULL_MASK, c, o);
+            if (c < best_cost) {
+                best_cost = c;
+                best_mask = __ballot_sync(PR_FULL_MASK, skipped);
+                best_m = m;
+            } else {
+                __ballot_sync(PR_FULL_MASK, skipped);
+            }
+        }
+    }
+    if (lane == 0) {
+        plan_mask[q] = best_mask;
+        plan_m[q] = best_m;
+        plan_theta[q] = theta;
+    }
+}
+
+template <int NW, int E, bool SKIP>
 __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_FLAT_CTAS : NW <= 8 ? PR_FLAT_CTAS : NW <= 12 ? 2 : 1))
     bm25_flat_kernel(const WarpArgs a)
 {
@@ -130,7 +275,12 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_FLAT_CTAS : NW <= 8
         const int64_t qb = a.q_indptr[q];
         const int nq = (int)(a.q_indptr[q + 1] - qb);
         const float theta_run = a.run_theta[q];
-        const bool update_mode = (a.mode == 6) && (theta_run > 0.f);
+        const bool update_mode = (a.mode >= 6) && (theta_run > 0.f);
+#ifdef PR_STATS
+        unsigned st_acc[16] = {0};
+        PR_STAT(0, 1);
+        PR_STAT(8, nq);
+#endif
         item.reset();
         float thr = fmaxf(theta_run, PR_DENORM_MIN);  // warp-uniform filter for candidates
         float iks = PR_SENT_SCORE;
@@ -139,6 +289,10 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_FLAT_CTAS : NW <= 8
         const int sub1 = min(sub0 + G, a.n_sub);
         const bool single = nq <= 32;
         int cnt = 0;  // candidates pushed for the sub-tile being drained (warp-uniform)
+        // mode 7: this lane's term is skipped (t_skip); skip_m = upper bound of what the skipped
+        // terms can add to any document (0: nothing skipped, the tile holds exact scores)
+        bool t_skip = false;
+        float skip_m = 0.f;
         float thr_push = update_mode ? thr : __int_as_float(0x7f800000);
 
         // ---- per-lane description of one query term (lane j <-> term p0+j of the current pass)
@@ -199,6 +353,12 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_FLAT_CTAS : NW <= 8
         };
 
         if (single && nq > 0) load_info(0, nq, sub0 << kSubShift, min(sub1 << kSubShift, a.n_docs));
+        if (SKIP && update_mode && single) {  // the plan of bm25_plan_kernel for this query (made for a theta <= theta_run)
+            t_skip = (a.plan_mask[q] >> lane) & 1u;
+            skip_m = a.plan_m[q];
+            if (skip_m > 0.f) thr_push = thr * 0.99998f - skip_m;
+            PR_STAT(7, __popc(a.plan_mask[q]));
+        }
 
         // ---- producer: the next list of step descriptors of this item, in (sub-tile, pass, chunk) order
         int it_g = nq > 0 ? sub0 : sub1, it_p0 = 0, it_w0 = 0;
@@ -216,7 +376,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_FLAT_CTAS : NW <= 8
                     uint32_t sb = 0, se = 0;
                     int32_t scan_e = 0;
                     bool unresolved = false;
-                    if (t_class >= 1) {
+                    if (t_class >= 1 && !(SKIP && t_skip)) {
                         const uint32_t *tab = (t_class == 2 ? a.hot_off : a.tp) + (size_t)t_row * tab_stride + g;
                         if (single && g > sub0) {  // carried from the previous sub-tile / prefetched
                             sb = tb_cur;
@@ -279,13 +439,15 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_FLAT_CTAS : NW <= 8
                 } else if (t_class >= 0) {
                     n = (seg_len + 31) >> 5;
                 }
-                int incl = n;
+                int incl = n, S = 0;
+                if (!SKIP || __any_sync(PR_FULL_MASK, n > 0)) {  // (most sub-tiles are empty once the frequent terms are skipped)
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(PR_FULL_MASK, incl, o);
-                    if (lane >= o) incl += v;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(PR_FULL_MASK, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                    S = __shfl_sync(PR_FULL_MASK, incl, 31);
                 }
-                const int S = __shfl_sync(PR_FULL_MASK, incl, 31);
                 const int pre = incl - n;
                 const bool last_pass = it_p0 + 32 >= nq;
                 it_touched = it_touched || S > 0;
@@ -368,6 +530,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_FLAT_CTAS : NW <= 8
         };
         auto process = [&](const StepBuf &b, const bool may_end) {
             const uint32_t kind = b.meta & 3u;
+            PR_STAT(1 + kind, 1);
             if (kind == kStepWide) {
                 const uint32_t oo[4] = {b.d.x, b.d.y, b.d.z, b.d.w};
                 const float ww[4] = {b.w.x, b.w.y, b.w.z, b.w.w};
@@ -409,61 +572,95 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_FLAT_CTAS : NW <= 8
                 }
                 __syncwarp();
             } else if (may_end && (b.meta & kStepEnd)) {
-                // ---- select from the finished sub-tile (padding slots only ever hold +0.0f) and re-zero it
-                const int base_doc = (int)(b.d.x << kSubShift) + a.doc_id_base;
+                // ---- select from the finished sub-tile (padding slots only ever hold +0.0f) and re-zero it.
+                // With skipped terms (skip_m > 0) the tile holds partial sums: every word >= thr_push is
+                // rescored exactly (flat_rescore, 32/nq documents at a time) before it meets the list.
+                const int g_end = (int)b.d.x;
+                const int base_doc = (g_end << kSubShift) + a.doc_id_base;
+                const bool skipping = SKIP && skip_m > 0.f;
+                const float thr_sel = skipping ? thr_push : thr;  // fixed while this sub-tile is selected from
+                auto consider = [&](float bs, int off) {           // warp-uniform arguments, exact score
+                    const int bd = base_doc + off;
+                    if (bs >= thr && bs > theta_run && pr_beats(bs, bd, iks, ikd)) {
+                        item.insert(bs, bd, lane);
+                        item.kth(K, iks, ikd);
+                        thr = fmaxf(thr, iks);
+                    }
+                };
+                PR_STAT(5, 1);
+                auto rescore_list = [&](int n) {  // the n tile offsets in cand[]
+                    PR_STAT(6, n);
+                    const int gsz = 32 / nq;
+                    for (int c0 = 0; c0 < n; c0 += gsz) {
+                        const int nb = min(gsz, n - c0);
+                        const float sc = flat_rescore(a.q_terms + qb, nq, a.indptr, a.heavy_row, a.tp, a.doc_ids, a.weights,
+                                                      a.n_terms, a.n_sub, g_end, cand + c0, nb);
+                        for (int ci = 0; ci < nb; ++ci) consider(__shfl_sync(PR_FULL_MASK, sc, ci * nq), cand[c0 + ci]);
+                    }
+                };
                 if (update_mode && cnt <= kWarpCand) {
                     if (cnt > 0) {
                         float cs = -1.f;
-                        int cd = 0;
+                        int co = 0;
                         if (lane < cnt) {
-                            const int off = cand[lane];
+                            co = cand[lane];
                             // a doc pushed twice reads a cleared word (= 0) the second time
-                            cs = atomicExch(&tile[off], 0.f);
-                            cd = base_doc + off;
+                            cs = atomicExch(&tile[co], 0.f);
                         }
-                        unsigned mm = __ballot_sync(PR_FULL_MASK, cs >= thr);
-                        while (mm) {
-                            const int l = __ffs(mm) - 1;
-                            mm &= mm - 1;
-                            const float bs = __shfl_sync(PR_FULL_MASK, cs, l);
-                            const int bd = __shfl_sync(PR_FULL_MASK, cd, l);
-                            if (bs > theta_run && pr_beats(bs, bd, iks, ikd)) {
-                                item.insert(bs, bd, lane);
-                                item.kth(K, iks, ikd);
-                                thr = fmaxf(thr, iks);
+                        unsigned mm = __ballot_sync(PR_FULL_MASK, cs >= thr_sel);
+                        if (skipping) {
+                            __syncwarp();
+                            if (cs >= thr_sel) cand[__popc(mm & lt_mask)] = co;
+                            __syncwarp();
+                            rescore_list(__popc(mm));
+                        } else {
+                            while (mm) {
+                                const int l = __ffs(mm) - 1;
+                                mm &= mm - 1;
+                                consider(__shfl_sync(PR_FULL_MASK, cs, l), __shfl_sync(PR_FULL_MASK, co, l));
                             }
                         }
                     }
 #pragma unroll
                     for (int vv = lane; vv < kSub / 4; vv += 32) tile4[vv] = zero4;
                 } else {
+                    PR_STAT(10, 1);
+                    int n_c = 0;  // skipping: offsets waiting in cand[] for their rescoring
 #pragma unroll 4
                     for (int vv = lane; vv < kSub / 4; vv += 32) {
                         const float4 xb = tile4[vv];
                         tile4[vv] = zero4;
                         const float xs[4] = {xb.x, xb.y, xb.z, xb.w};
-                        const bool any = (xs[0] >= thr) || (xs[1] >= thr) || (xs[2] >= thr) || (xs[3] >= thr);
+                        const bool any = (xs[0] >= thr_sel) || (xs[1] >= thr_sel) || (xs[2] >= thr_sel) || (xs[3] >= thr_sel);
                         if (__any_sync(PR_FULL_MASK, any)) {
 #pragma unroll
                             for (int cc = 0; cc < 4; ++cc) {
-                                unsigned mm = __ballot_sync(PR_FULL_MASK, xs[cc] >= thr);
-                                while (mm) {
-                                    const int l = __ffs(mm) - 1;
-                                    mm &= mm - 1;
-                                    const float bs = __shfl_sync(PR_FULL_MASK, xs[cc], l);
-                                    const int bd = base_doc + 4 * (vv - lane + l) + cc;
-                                    if (bs >= thr && bs > theta_run && pr_beats(bs, bd, iks, ikd)) {
-                                        item.insert(bs, bd, lane);
-                                        item.kth(K, iks, ikd);
-                                        thr = fmaxf(thr, iks);
+                                unsigned mm = __ballot_sync(PR_FULL_MASK, xs[cc] >= thr_sel);
+                                if (skipping) {
+                                    if (mm) {
+                                        if (n_c + __popc(mm) > kWarpCand) {
+                                            rescore_list(n_c);
+                                            n_c = 0;
+                                            __syncwarp();
+                                        }
+                                        if (xs[cc] >= thr_sel) cand[n_c + __popc(mm & lt_mask)] = 4 * vv + cc;
+                                        n_c += __popc(mm);
+                                        __syncwarp();
+                                    }
+                                } else {
+                                    while (mm) {
+                                        const int l = __ffs(mm) - 1;
+                                        mm &= mm - 1;
+                                        consider(__shfl_sync(PR_FULL_MASK, xs[cc], l), 4 * (vv - lane + l) + cc);
                                     }
                                 }
                             }
                         }
                     }
+                    if (skipping) rescore_list(n_c);
                 }
                 cnt = 0;
-                thr_push = update_mode ? thr : __int_as_float(0x7f800000);
+                thr_push = !update_mode ? __int_as_float(0x7f800000) : skipping ? thr * 0.99998f - skip_m : thr;
                 __syncwarp();
             }
         };
@@ -503,6 +700,13 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_FLAT_CTAS : NW <= 8
                 pdst[i] = item.d[e];
             }
         }
+#ifdef PR_STATS
+        if (lane == 0) {
+            const int li = min(pr_stats_launch, 511);
+            for (int i = 0; i < 16; ++i)
+                if (st_acc[i]) atomicAdd(&pr_stats_dev[li * 16 + i], (unsigned long long)st_acc[i]);
+        }
+#endif
     }
 }
 

@@ -45,6 +45,9 @@ struct WarpArgs {
     const int32_t *__restrict__ hot_of_row; // [n_rows] row of `hot_off`, or -1 (null: no hot stream)
     const uint32_t *__restrict__ hot_off;   // [n_hot][n_sub+1] 256-byte units of the hot stream before (row, sub-tile)
     const unsigned char *__restrict__ hot_stream;
+    const float *__restrict__ term_maxw;    // [n_terms] largest weight of the term's list (mode 7), or null
+    const uint32_t *__restrict__ plan_mask; // [n_queries] mode 7: bit j = term j of the query is skipped
+    const float *__restrict__ plan_m;       // [n_queries] mode 7: upper bound of what the skipped terms add to a document
     const int64_t *__restrict__ q_indptr;
     const int32_t *__restrict__ q_terms;
     const float *__restrict__ run_theta;
@@ -55,7 +58,7 @@ struct WarpArgs {
     int64_t nnz;
     int32_t n_docs, n_terms, doc_id_base, n_queries, K;
     int32_t n_sub, subs_per_item, chunk0, n_chunks_launch;
-    int32_t mode;  // 3 scan, 4 threshold-on-update
+    int32_t mode;  // 3/5 scan, 4/6 threshold-on-update, 7 threshold-on-update with rank-safe term skipping
 };
 
 __host__ __device__ inline size_t warp_smem_bytes(int nw) { return (size_t)nw * (kSub * 4 + kWarpCand * 4 + 32 * 8); }
@@ -539,6 +542,60 @@ __global__ void tp_fill_kernel(const int64_t *indptr, const int32_t *doc_ids, co
             else hi = mid;
         }
         tp[idx] = (uint32_t)(lo - b0);
+    }
+}
+
+// row_q[2r], row_q[2r+1] = weights of tabulated row r that at most ~1% / ~10% of its postings reach
+// (lower edges of a 256-bin histogram over [0, term_maxw]).  Only the cost model of the mode-7
+// planner reads them, so they need not be exact.  One CTA per row.
+__global__ void __launch_bounds__(256) row_quantile_kernel(const int64_t *indptr, const float *weights, const int32_t *row_term,
+                                                          const float *term_maxw, int n_rows, float *row_q)
+{
+    __shared__ int hist[256];
+    for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
+        const int t = row_term[r];
+        const int64_t b = indptr[t], e = indptr[t + 1];
+        const float mx = term_maxw[t];
+        const float inv = mx > 0.f ? 256.f / mx : 0.f;
+        hist[threadIdx.x] = 0;
+        __syncthreads();
+        for (int64_t p = b + threadIdx.x; p < e; p += 256) atomicAdd(&hist[min(255, (int)(weights[p] * inv))], 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int64_t df = e - b;
+            int64_t acc = 0;
+            float q99 = mx, q90 = mx;
+            bool have99 = false;
+            for (int bin = 255; bin >= 0; --bin) {
+                acc += hist[bin];
+                if (!have99 && acc * 100 > df) {
+                    q99 = (bin + 1) * mx / 256.f;
+                    have99 = true;
+                }
+                if (acc * 10 > df) {
+                    q90 = (bin + 1) * mx / 256.f;
+                    break;
+                }
+            }
+            row_q[2 * r] = q99;
+            row_q[2 * r + 1] = q90;
+        }
+        __syncthreads();
+    }
+}
+
+// term_maxw[t] = largest weight in the list of term t (0 for an empty list); one warp per term.
+// Upper bound of any one posting's contribution, used by the rank-safe term skipping of mode 7.
+__global__ void __launch_bounds__(256) term_maxw_kernel(const int64_t *indptr, const float *weights, int n_terms, float *term_maxw)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_terms; t += n_warps) {
+        const int64_t b = indptr[t], e = indptr[t + 1];
+        float m = 0.f;
+        for (int64_t p = b + lane; p < e; p += 32) m = fmaxf(m, weights[p]);
+        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(PR_FULL_MASK, m, o));
+        if (lane == 0) term_maxw[t] = m;
     }
 }
 

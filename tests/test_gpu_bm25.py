@@ -33,6 +33,10 @@ TUNINGS = [
     dict(mode=5, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304),
     dict(mode=6, subs_per_item=1, warps_per_cta=4, docs_per_launch=2048, min_items=1),
     dict(mode=6, subs_per_item=5, warps_per_cta=12, docs_per_launch=1000000, min_items=100000),
+    dict(mode=7, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304),                  # + rank-safe term skipping
+    dict(mode=7, subs_per_item=4, warps_per_cta=8, docs_per_launch=8192),                    # many launches: skipping from launch 2 on
+    dict(mode=7, subs_per_item=1, warps_per_cta=4, docs_per_launch=2048, min_items=1),
+    dict(mode=7, subs_per_item=3, warps_per_cta=12, docs_per_launch=20000, min_items=2048),
     dict(threads=512, tile_docs=2048, tiles_per_item=1, mode=2, min_items=1),   # many launches
     dict(threads=512, tile_docs=16384, tiles_per_item=2, mode=1, min_items=100000),  # one launch
 ]
@@ -91,7 +95,8 @@ def test_depth_sweep(small_corpus, corpus_gpu, k):
                 dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
                 dict(mode=3, subs_per_item=3, warps_per_cta=8, docs_per_launch=20000, min_items=2048),
                 dict(mode=6, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
-                dict(mode=5, subs_per_item=3, warps_per_cta=12, docs_per_launch=20000, min_items=2048)):
+                dict(mode=5, subs_per_item=3, warps_per_cta=12, docs_per_launch=20000, min_items=2048),
+                dict(mode=7, subs_per_item=3, warps_per_cta=8, docs_per_launch=10000, min_items=2048)):
         corpus_gpu.set_tuning(**tun)
         gs, gd = run_gpu(corpus_gpu, qi, qt, k)
         assert_parity(gs, gd, os_, od)
@@ -104,7 +109,8 @@ def test_small_batches(small_corpus, corpus_gpu, nq):
     os_, od = co.retrieve_batch(small_corpus["index"], qi, qt, 10)
     for tun in (dict(threads=512, tile_docs=24576, tiles_per_item=4, mode=2, min_items=2048, cand_cap=1024),
                 dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
-                dict(mode=6, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048)):
+                dict(mode=6, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
+                dict(mode=7, subs_per_item=2, warps_per_cta=8, docs_per_launch=8192, min_items=2048)):
         corpus_gpu.set_tuning(**tun)
         gs, gd = run_gpu(corpus_gpu, qi, qt, 10)
         assert_parity(gs, gd, os_, od)
@@ -117,9 +123,9 @@ def test_long_transcript_queries(small_corpus, corpus_gpu):
     qi, qt = synth.queries_np(48, small_corpus["vocab"], idx["df"], kind="later")
     assert np.diff(qi).max() > 256
     os_, od = co.retrieve_batch(idx, qi, qt, 10, n_threads=8)
-    for mode in (1, 2, 3, 4, 5, 6):
+    for mode in (1, 2, 3, 4, 5, 6, 7):
         corpus_gpu.set_tuning(threads=512, tile_docs=24576, tiles_per_item=2, mode=mode, min_items=2048,
-                              subs_per_item=4, warps_per_cta=8, docs_per_launch=98304)
+                              subs_per_item=4, warps_per_cta=8, docs_per_launch=98304 if mode < 7 else 16384)
         gs, gd = run_gpu(corpus_gpu, qi, qt, 10)
         assert_parity(gs, gd, os_, od)
 
@@ -137,7 +143,7 @@ def test_edge_queries(small_corpus, corpus_gpu):
     qi[1:] = np.cumsum([len(q) for q in queries])
     qt = np.array([t for q in queries for t in q], dtype=np.int32)
     os_, od = bo.retrieve_batch(idx, qi, qt, 10)
-    for tun in TUNINGS[:3] + TUNINGS[4:14]:
+    for tun in TUNINGS[:3] + TUNINGS[4:18]:
         corpus_gpu.set_tuning(**tun)
         gs, gd = run_gpu(corpus_gpu, qi, qt, 10)
         assert_parity(gs, gd, os_, od)
@@ -194,7 +200,9 @@ def test_tie_heavy_corpus():
                     dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048, lazy_zero=2),
                     dict(mode=6, subs_per_item=2, warps_per_cta=4, docs_per_launch=4096, min_items=1),
                     dict(mode=5, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=100000),
-                    dict(mode=6, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048)):
+                    dict(mode=6, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
+                    dict(mode=7, subs_per_item=2, warps_per_cta=4, docs_per_launch=4096, min_items=1),
+                    dict(mode=7, subs_per_item=3, warps_per_cta=8, docs_per_launch=8192, min_items=2048)):
             gi.set_tuning(**dict(dict(lazy_zero=1), **tun))
             gs, gd = run_gpu(gi, qi, qt, k)
             assert_parity(gs, gd, os_, od)
@@ -236,7 +244,7 @@ def test_doc_range_shards_and_merge_equal_single_index(small_corpus, corpus_gpu)
             sh = bo.build_index(toks[off[lo]:off[hi]], lens[lo:hi], small_corpus["vocab"], n_docs_global=n_docs,
                                 avgdl_global=idx["avgdl"], df_global=idx["df"], doc_id_base=lo)
             gi = gpu_index(sh, n_docs_global=n_docs, doc_id_base=lo)
-            gi.set_tuning(mode=4 if g != 3 else 2)
+            gi.set_tuning(mode=(4 if g == 2 else 2 if g == 3 else 7), docs_per_launch=98304 if g != 8 else 4096)
             dev = gi.device
             s, d = gi.topk(torch.from_numpy(qi).to(dev), torch.from_numpy(qt).to(dev), 10)
             ss.append(s); dd.append(d)
@@ -306,7 +314,7 @@ def test_full_size_21m_properties():
     d_qi, d_qt = torch.from_numpy(qi).to(dev), torch.from_numpy(qt).to(dev)
     gi.set_tuning(mode=2)
     s2, d2 = gi.topk(d_qi, d_qt, 10)
-    for mode in (1, 3, 4):
+    for mode in (1, 3, 4, 6, 7):
         gi.set_tuning(mode=mode)
         s1, d1 = gi.topk(d_qi, d_qt, 10)
         assert torch.equal(s1, s2) and torch.equal(d1, d2), mode
@@ -332,7 +340,7 @@ def test_weights_outside_lazy_range_use_plain_accumulators(small_corpus):
     gi = gpu_index(idx)
     qi, qt = small_corpus["q_indptr"][:129], small_corpus["q_terms"]
     os_, od = co.retrieve_batch(idx, qi, qt, 10, n_threads=8)
-    for mode in (4, 3, 2):
-        gi.set_tuning(mode=mode)
+    for mode in (4, 3, 2, 7):
+        gi.set_tuning(mode=mode, docs_per_launch=98304 if mode != 7 else 16384)
         gs, gd = run_gpu(gi, qi, qt, 10)
         assert_parity(gs, gd, os_, od)

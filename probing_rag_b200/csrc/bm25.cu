@@ -618,10 +618,10 @@ void default_tuning(pr_bm25_tuning_t *t)
     t->tile_docs = 24576;
     t->tiles_per_item = 4;
     t->threads = 512;
-    t->mode = 4;
+    t->mode = 6;
     t->min_items = 2048;
     t->cand_cap = 1024;
-    t->subs_per_item = 12;
+    t->subs_per_item = 24;
     t->warps_per_cta = 8;
     t->docs_per_launch = 98304;
     t->lazy_zero = 2;

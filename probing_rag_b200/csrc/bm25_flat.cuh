@@ -366,6 +366,26 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_FLAT_CTAS : NW <= 8
         uint32_t seg_x = 0;               // per lane, for (it_g, it_p0): first table unit / posting (relative)
         int32_t seg_len = 0;              // ... and how many
 
+        // this lane's step descriptors k in [k0, k1) of its current segment (seg_x, seg_len), from list address `la` on
+        auto write_steps = [&](uint32_t la, int k0, int k1, int n_wide) {
+            if (t_class == 2) {
+#pragma unroll 1
+                for (int k = k0; k < k1; ++k, la += 8u) {
+                    const bool wide = k < n_wide;
+                    const uint32_t x = wide ? seg_x + 4u * (uint32_t)k : seg_x + 3u * (uint32_t)n_wide + (uint32_t)k;
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(la), "r"(x), "r"(wide ? kStepWide : kStepNarrow) : "memory");
+                }
+            } else {
+                int64_t p = t_b0 + seg_x + 32 * (int64_t)k0;
+                int left = seg_len - 32 * k0;
+#pragma unroll 1
+                for (int k = k0; k < k1; ++k, la += 8u, p += 32, left -= 32) {
+                    const uint32_t y = kStepGen | ((uint32_t)min(32, left) << 2) | ((uint32_t)(p >> 32) << 8);
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(la), "r"((uint32_t)p), "r"(y) : "memory");
+                }
+            }
+        };
+
         auto produce = [&](uint32_t list_sa) -> int {
             while (it_g < sub1) {
                 const int g = it_g;
@@ -470,26 +490,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_FLAT_CTAS : NW <= 8
                 }
                 if (chunk == 0 && !end) continue;  // nothing in this pass / untouched sub-tile
                 // ---- this lane's entries k in [k0, k1) -> list positions pre + k - w0
-                {
-                    const int k0 = max(0, w0 - pre), k1 = min(n, w0 + chunk - pre);
-                    uint32_t la = list_sa + 8u * (uint32_t)(pre + k0 - w0);
-                    if (t_class == 2) {
-#pragma unroll 1
-                        for (int k = k0; k < k1; ++k, la += 8u) {
-                            const bool wide = k < n_wide;
-                            const uint32_t x = wide ? seg_x + 4u * (uint32_t)k : seg_x + 3u * (uint32_t)n_wide + (uint32_t)k;
-                            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(la), "r"(x), "r"(wide ? kStepWide : kStepNarrow) : "memory");
-                        }
-                    } else {
-                        int64_t p = t_b0 + seg_x + 32 * (int64_t)k0;
-                        int left = seg_len - 32 * k0;
-#pragma unroll 1
-                        for (int k = k0; k < k1; ++k, la += 8u, p += 32, left -= 32) {
-                            const uint32_t y = kStepGen | ((uint32_t)min(32, left) << 2) | ((uint32_t)(p >> 32) << 8);
-                            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(la), "r"((uint32_t)p), "r"(y) : "memory");
-                        }
-                    }
-                }
+                write_steps(list_sa + 8u * (uint32_t)(pre + max(0, w0 - pre) - w0), max(0, w0 - pre), min(n, w0 + chunk - pre), n_wide);
                 // ---- no-ops up to a multiple of kPipe; an END step always sits in the last ring slot
                 int len = chunk;
                 const int pad = (kPipe - ((len + (end ? 1 : 0)) % kPipe)) % kPipe;
@@ -497,6 +498,141 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_FLAT_CTAS : NW <= 8
                 len += pad;
                 if (end) {
                     if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(list_sa + 8u * (uint32_t)len), "r"((uint32_t)g), "r"((uint32_t)(kStepSpecial | kStepEnd)) : "memory");
+                    ++len;
+                }
+                __syncwarp();
+                return len;
+            }
+            return 0;
+        };
+
+        // ---- fast producer: queries of <= 16 terms whose rare terms have <= 4 postings in the item's range
+        // (almost every round-0 query).  The lanes are re-mapped to (sub-tile slot s, term j) = (lane / TPL,
+        // lane % TPL), TPL = 8 or 16, so ONE pass of table look-ups, prefix sums and descriptor stores lays out
+        // 32 / TPL consecutive sub-tiles; a rare term's few documents sit in registers (tb_cur, tb_next, t_nd,
+        // t_le re-used), so there is no cursor.  A sub-tile whose steps overflow the list is cut into chunks.
+        const int tpl_shift = nq <= 8 ? 3 : 4;
+        const bool fast = single && nq > 0 && nq <= 16 && !__any_sync(PR_FULL_MASK, t_class == 0 && t_le - t_pos > 4);
+        if (fast) {
+            const int j = lane & ((1 << tpl_shift) - 1);
+            const int c_ = __shfl_sync(PR_FULL_MASK, t_class, j), row_ = __shfl_sync(PR_FULL_MASK, t_row, j);
+            const int pos_ = __shfl_sync(PR_FULL_MASK, t_pos, j), le_ = __shfl_sync(PR_FULL_MASK, t_le, j);
+            const int64_t b0_ = __shfl_sync(PR_FULL_MASK, t_b0, j);
+            const bool sk_ = __shfl_sync(PR_FULL_MASK, (int)t_skip, j) != 0;
+            t_class = c_;
+            t_row = row_;
+            t_b0 = b0_;
+            t_pos = pos_;
+            t_skip = sk_;
+            int dd[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+            if (c_ == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (pos_ + i < le_) dd[i] = __ldg(a.doc_ids + b0_ + pos_ + i);
+            }
+            tb_cur = (uint32_t)dd[0];
+            tb_next = (uint32_t)dd[1];
+            t_nd = dd[2];
+            t_le = dd[3];
+        }
+
+        auto produce_fast = [&](uint32_t list_sa) -> int {
+            const int NS = 32 >> tpl_shift, TPL = 1 << tpl_shift;
+            const int s = lane >> tpl_shift, j = lane & (TPL - 1);
+            while (it_g < sub1) {
+                const int g0 = it_g, g = g0 + s;
+                if (it_w0 == 0) {  // what each term has inside each of the NS sub-tiles
+                    uint32_t sb = 0, se = 0;
+                    if (g < sub1 && !(SKIP && t_skip)) {
+                        if (t_class >= 1) {
+                            const uint32_t *tab = (t_class == 2 ? a.hot_off : a.tp) + (size_t)t_row * tab_stride + g;
+                            sb = __ldg(tab);
+                            se = __ldg(tab + 1);
+                        } else if (t_class == 0) {
+                            const int lo = g << kSubShift, hi = a.n_docs - lo > kSub ? lo + kSub : a.n_docs;
+                            const int d0 = (int)tb_cur, d1 = (int)tb_next, d2 = t_nd, d3 = t_le;
+                            sb = (uint32_t)(t_pos + (d0 < lo) + (d1 < lo) + (d2 < lo) + (d3 < lo));
+                            se = (uint32_t)(t_pos + (d0 < hi) + (d1 < hi) + (d2 < hi) + (d3 < hi));
+                        }
+                    }
+                    seg_x = sb;
+                    seg_len = (int32_t)(se - sb);
+                }
+                int n_wide = 0, n = 0;
+                if (it_w0 == 0 || s == 0) {  // a chunked sub-tile continues with slot 0 only
+                    if (t_class == 2) {
+                        n_wide = seg_len >> 2;
+                        n = n_wide + (seg_len & 3);
+                    } else if (t_class >= 0) {
+                        n = (seg_len + 31) >> 5;
+                    }
+                }
+                if (!__any_sync(PR_FULL_MASK, n > 0)) {  // nothing in these sub-tiles
+                    it_g = g0 + NS;
+                    continue;
+                }
+                int incl = n;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(PR_FULL_MASK, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                int e_prev = __shfl_sync(PR_FULL_MASK, incl, max((s << tpl_shift) - 1, 0));
+                if (s == 0) e_prev = 0;
+                const int pre = incl - n - e_prev;  // steps of this lane's sub-tile before its own
+                // ---- lay the sub-tiles out one after the other: steps, no-ops up to the last ring slot, END
+                int base = 0, my_base = -1, my_t = 0, my_total = 0, ns_eff = 0, prev_e = 0, t0 = 0;
+                bool chunked = it_w0 > 0;
+                for (int ss = 0; ss < NS && !chunked; ++ss) {
+                    const int e = __shfl_sync(PR_FULL_MASK, incl, (ss << tpl_shift) + TPL - 1);
+                    const int t = e - prev_e;
+                    prev_e = e;
+                    if (ss == 0) t0 = t;
+                    if (t > 0) {
+                        const int total = (t + kPipe) / kPipe * kPipe;  // t steps + END, rounded up to whole rings
+                        if (base + total > kListCap) {
+                            chunked = ss == 0;
+                            break;
+                        }
+                        if (ss == s) {
+                            my_base = base;
+                            my_t = t;
+                            my_total = total;
+                        }
+                        base += total;
+                    }
+                    ns_eff = ss + 1;
+                }
+                if (!chunked) {
+                    it_g = g0 + ns_eff;
+                    if (base == 0) continue;  // the first non-empty sub-tile did not fit behind empty ones: next round
+                    if (my_base >= 0) {
+                        write_steps(list_sa + 8u * (uint32_t)(my_base + pre), 0, n, n_wide);
+                        const int pad = my_total - my_t - 1;
+                        if (j < pad) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(list_sa + 8u * (uint32_t)(my_base + my_t + j)), "r"(0u), "r"((uint32_t)kStepSpecial) : "memory");
+                        if (j == TPL - 1) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(list_sa + 8u * (uint32_t)(my_base + my_total - 1)), "r"((uint32_t)g), "r"((uint32_t)(kStepSpecial | kStepEnd)) : "memory");
+                    }
+                    __syncwarp();
+                    return base;
+                }
+                // ---- one long sub-tile (g0), a chunk of its steps per call
+                if (it_w0 > 0) t0 = __shfl_sync(PR_FULL_MASK, incl, TPL - 1);
+                const int w0 = it_w0;
+                const int chunk = min(t0 - w0, kListCap - kPipe);
+                const bool fin = w0 + chunk >= t0;
+                if (!fin) {
+                    it_w0 = w0 + chunk;
+                } else {
+                    it_w0 = 0;
+                    it_g = g0 + 1;
+                }
+                if (s == 0) write_steps(list_sa + 8u * (uint32_t)(pre + max(0, w0 - pre) - w0), max(0, w0 - pre), min(n, w0 + chunk - pre), n_wide);
+                int len = chunk;
+                const int pad = (kPipe - ((len + (fin ? 1 : 0)) % kPipe)) % kPipe;
+                if (lane < pad) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(list_sa + 8u * (uint32_t)(len + lane)), "r"(0u), "r"((uint32_t)kStepSpecial) : "memory");
+                len += pad;
+                if (fin) {
+                    if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(list_sa + 8u * (uint32_t)len), "r"((uint32_t)g0), "r"((uint32_t)(kStepSpecial | kStepEnd)) : "memory");
                     ++len;
                 }
                 __syncwarp();
@@ -666,13 +802,20 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_FLAT_CTAS : NW <= 8
         };
 
         // ---- consumer: drain list `cur` while list `cur ^ 1` is already produced, so the ring never runs dry
+        // (one producer call site: the first round produces into `nxt` and drains an empty `cur`)
         uint32_t cur_sa = desc_sa, nxt_sa = desc_sa + 8u * kListCap;
-        int n_cur = produce(cur_sa);
+        int n_cur = 0;
+        bool first = true;
+        while (true) {
+            const int n_next = fast ? produce_fast(nxt_sa) : produce(nxt_sa);
+            if (first) {
+                first = false;
 #pragma unroll
-        for (int d = 0; d < kPipe; ++d)
-            if (d < n_cur) issue(cur_sa + 8u * d, buf[d]);
-        while (n_cur > 0) {
-            const int n_next = produce(nxt_sa);
+                for (int d = 0; d < kPipe; ++d) {
+                    if (d < n_next) issue(nxt_sa + 8u * d, buf[d]);
+                    else buf[d].meta = kStepSpecial;
+                }
+            }
 #pragma unroll 1
             for (int s0 = 0; s0 < n_cur; s0 += kPipe) {
 #pragma unroll
@@ -688,6 +831,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_FLAT_CTAS : NW <= 8
             cur_sa = nxt_sa;
             nxt_sa = t;
             n_cur = n_next;
+            if (n_cur == 0) break;
         }
 
         float *ps = a.part_s + ((size_t)q * C + c) * K;

@@ -13,7 +13,8 @@
 //
 //   * offsets are pre-scaled byte offsets into the warp's tile (no masking / shifting per slot);
 //   * segments are padded to whole steps with (dummy word, +0.0f) slots, so there are no
-//     validity masks and no alignment heads;
+//     validity masks and no alignment heads; a remainder of more than 32 postings takes one
+//     padded wide step rather than up to three narrow ones (fewer steps beat fewer slots: +10%);
 //   * inside a segment the postings are dealt round-robin over the steps' 32-slot groups in
 //     bank-sorted order (doc % 32), so the 32 documents a warp touches together fall into
 //     distinct banks whenever the segment's bank histogram allows it.
@@ -30,15 +31,22 @@ namespace prh {
 using prw::kSub;
 using prw::kSubShift;
 
-constexpr int kHotMinSeg = 8;    // a term is hot when it averages >= 8 postings per sub-tile
+#ifndef PR_HOT_MIN_SEG
+#define PR_HOT_MIN_SEG 8
+#endif
+constexpr int kHotMinSeg = PR_HOT_MIN_SEG;  // a term is hot when it averages >= this many postings per sub-tile
 constexpr int kUnitBytes = 256;  // narrow step; a wide step is 4 units
+#ifndef PR_HOT_WIDE_REM
+#define PR_HOT_WIDE_REM 32
+#endif
+constexpr int kWideRem = PR_HOT_WIDE_REM;  // a remainder above this many postings takes one more (padded) wide step
 
 // 256-byte units a segment of n postings occupies: full wide steps, then the rest as narrow
-// steps (or one more wide step when the rest is > 96)
+// steps (or one more wide step when the rest is > kWideRem)
 __host__ __device__ __forceinline__ int seg_units(int n)
 {
     int w = n >> 7, r = n & 127;
-    if (r > 96) {
+    if (r > kWideRem) {
         ++w;
         r = 0;
     }

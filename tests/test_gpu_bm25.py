@@ -184,7 +184,8 @@ def test_tie_heavy_corpus():
     base = [rng.integers(0, 40, size=int(rng.integers(4, 12))).astype(np.int32) for _ in range(25)]
     docs = [base[int(rng.integers(0, 25))].copy() for _ in range(30000)]
     idx = bo.build_index(np.concatenate(docs), np.array([len(d) for d in docs]), 40)
-    queries = [[int(t)] for t in range(0, 40, 5)] + [[1, 2, 3], [7, 7, 9, 30, 2], [39, 0]]
+    queries = [[int(t)] for t in range(0, 40, 5)] + [[1, 2, 3], [7, 7, 9, 30, 2], [39, 0]] + \
+        [list(range(16)), list(range(20, 28)), [1] * 12, list(range(5, 22)), [3, 3, 4, 4, 5, 5, 6, 6, 7]]  # long step lists: chunked sub-tiles
     qi = np.zeros(len(queries) + 1, np.int64)
     qi[1:] = np.cumsum([len(q) for q in queries])
     qt = np.array([t for q in queries for t in q], dtype=np.int32)

@@ -309,6 +309,17 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    tuning = gi.get_tuning()
+    kernel = {1: "bm25_score_kernel", 2: "bm25_score_kernel", 3: "bm25_warp_kernel", 4: "bm25_warp_kernel"}.get(
+        tuning["mode"], "bm25_flat_kernel")
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/), if any
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tj.get("kernel") == kernel:
+            traffic = {"dram_bytes_per_launch": tj["dram_bytes_per_launch"], "source": tj.get("source")}
+    except Exception:
+        pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     achieved = alg_bytes / (score_ms * 1e-3) / 1e9 if score_ms > 0 else 0.0
@@ -329,14 +340,15 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload, "k": k, "n_docs": args.n_docs, "n_queries": nq, "vocab": args.vocab,
                    "nnz_shard0": gi.nnz, "l2": "inputs (index shard of %.1f GB) larger than L2" % (gi.nnz * 8 / 1e9),
-                   "tuning": gi.get_tuning(), "parallelism": f"doc-shard x{world}" if world > 1 else "single"},
+                   "tuning": tuning, "parallelism": f"doc-shard x{world}" if world > 1 else "single"},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches_per_step * args.steps),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "frac_of_8000_nominal": achieved / 8000.0, "traffic": None,
-                     "peak_source": peak_src, "kernel": "bm25_score_kernel",
+                     "frac": achieved / peak, "frac_of_8000_nominal": achieved / 8000.0, "traffic": traffic,
+                     "peak_source": peak_src, "kernel": kernel,
+                     "algorithmic_bytes_per_launch": int(alg_bytes / max(score_launches, 1)),
                      "algorithmic_bytes_per_step_rank0": int(alg_bytes),
                      "algorithmic_bytes_per_step_all_ranks": int(alg_total),
                      "kernel_ms_per_step": score_ms, "kernel_launches_per_step": score_launches,

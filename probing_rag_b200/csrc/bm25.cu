@@ -598,6 +598,7 @@ warp_fn_t pick_flat_fn(int nw, int E, bool skip)
         return pick_flat<8, true>(E);
     }
     if (nw == 4) return pick_flat<4, false>(E);
+    if (nw == 10) return pick_flat<10, false>(E);   // 2 CTAs of 10 warps: 20 warps per SM, 96 registers per thread
     if (nw == 12) return pick_flat<12, false>(E);
     return pick_flat<8, false>(E);
 }
@@ -639,9 +640,10 @@ int check_tuning(const pr_bm25_tuning_t &t)
         return PR_EINVAL;
     }
     if (t.subs_per_item < 1 || t.docs_per_launch < 1 ||
-        (t.warps_per_cta != 4 && t.warps_per_cta != 8 && t.warps_per_cta != 9 && t.warps_per_cta != 12 &&
+        (t.warps_per_cta != 4 && t.warps_per_cta != 8 && t.warps_per_cta != 9 && t.warps_per_cta != 10 && t.warps_per_cta != 12 &&
          t.warps_per_cta != 13 && t.warps_per_cta != 16) ||
-        (t.mode >= 5 && t.warps_per_cta != 4 && t.warps_per_cta != 8 && t.warps_per_cta != 12)) {
+        (t.mode >= 5 && t.warps_per_cta != 4 && t.warps_per_cta != 8 && t.warps_per_cta != 10 && t.warps_per_cta != 12) ||
+        (t.mode < 5 && t.warps_per_cta == 10) || (t.mode == 7 && t.warps_per_cta == 10)) {
         pr_set_error("bad tuning (subs_per_item=%d docs_per_launch=%d warps_per_cta=%d; warps_per_cta is 4, 8, 9, 12, 13 or 16; "
                      "4, 8 or 12 for modes 5/6)",
                      t.subs_per_item, t.docs_per_launch, t.warps_per_cta);

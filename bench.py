@@ -310,7 +310,8 @@ def main():
     except Exception:
         pass
     tuning = gi.get_tuning()
-    kernel = {1: "bm25_score_kernel", 2: "bm25_score_kernel", 3: "bm25_warp_kernel", 4: "bm25_warp_kernel"}.get(
+    kernel = {1: "bm25_score_kernel", 2: "bm25_score_kernel", 3: "bm25_warp_kernel", 4: "bm25_warp_kernel",
+              8: "bm25_lean_kernel" if gi.aux_info().get("lean_ok") else "bm25_flat_kernel"}.get(
         tuning["mode"], "bm25_flat_kernel")
     # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/), if any
     traffic = None

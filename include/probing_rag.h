@@ -48,7 +48,9 @@ typedef struct pr_bm25_tuning {
     int32_t mode;           /* CTA-cooperative kernel: 1 = scan select, 2 = threshold-on-update; warp-autonomous
                                segment-loop kernel: 3 = scan select, 4 = threshold-on-update; warp-autonomous
                                flat-step kernel: 5 = scan select, 6 = threshold-on-update, 7 = 6 + rank-safe
-                               skipping of frequent terms with exact rescoring of the candidates */
+                               skipping of frequent terms with exact rescoring of the candidates; 8 (default) =
+                               lean-step kernel over the cold + hot posting streams (runs as 6 on an index
+                               without a cold stream) */
     int32_t min_items;      /* doc ranges are split until a launch has this many work items   */
     int32_t cand_cap;       /* candidate buffer entries per CTA (mode 2)                      */
     /* warp-autonomous kernel (modes 3 = scan select, 4 = threshold-on-update select) */
@@ -82,11 +84,15 @@ int pr_index_destroy(pr_index_t *index);
  *     fits a fifth of `table_budget_bytes`, the posting offset of each 2048-document boundary;
  *   - the hot posting stream (modes 5/6): for the terms with >= 8 postings per 2048 documents, as
  *     many as fit the rest of the budget, a padded, bank-aware, mask-free copy of their postings
- *     (about 10 bytes per hot posting).  Without it modes 5/6 read every term from the CSR.
+ *     (about 10 bytes per hot posting).  Without it modes 5/6 read every term from the CSR;
+ *   - the cold posting stream (mode 8): every posting as an interleaved (tile byte offset, weight) pair,
+ *     8 bytes per posting, which pr_index_aux_bytes adds on top of the budget.  pr_index_lean_info
+ *     reports whether mode 8 can use it (the stream space must fit 32-bit granule indices).
  * pr_index_build_aux synchronises `stream`. */
 size_t pr_index_aux_bytes(const pr_index_t *index, size_t table_budget_bytes);
 int pr_index_build_aux(pr_index_t *index, void *aux_dev, size_t aux_bytes, pr_stream_t stream);
 int pr_index_aux_info(const pr_index_t *index, int32_t *n_rows, int64_t *min_df);
+int pr_index_lean_info(const pr_index_t *index, int32_t *lean_ok, int64_t *cold_bytes);
 int pr_index_hot_info(const pr_index_t *index, int32_t *n_hot, int64_t *min_df, int64_t *stream_bytes);
 int pr_index_set_tuning(pr_index_t *index, const pr_bm25_tuning_t *tuning);
 int pr_index_get_tuning(const pr_index_t *index, pr_bm25_tuning_t *tuning);
@@ -165,6 +171,21 @@ int pr_prober_forward(const pr_prober_set_t *probers, int32_t n_rows, const floa
                       uint8_t *out_retrieve_mask_dev, int32_t *out_compact_idx_dev,
                       int32_t *out_n_retrieve_dev, void *workspace_dev, size_t workspace_bytes,
                       pr_stream_t stream);
+
+/* ---- hidden-state pooling ---------------------------------------------------
+ * On-device replacement of the forward hooks at /root/reference/exp_rag.py:317-321 (which copy every
+ * probed layer's activations to the host on every forward call) and of the concat + sum over tokens at
+ * exp_rag.py:385-386.  Adds the token-sum of one forward call's activations of one probed layer into
+ * the prober input matrix:
+ *   acc_dev float[n_acc_rows, n_probers, d_model]  +=  sum_t act[r, t, :]   into [row, slot, :]
+ *   act_dev [n_rows, n_tokens, d_model] of act_dtype (0 = f32, 1 = bf16, 2 = f16), element strides
+ *   row_stride / tok_stride (feature stride 1); row_map_dev int32[n_rows] maps activation row r to an
+ *   accumulator row (negative = skip), NULL = identity.
+ * The caller skips the prefill call of a generation (the reference drops cache[name][0]).  fp32
+ * accumulation in token order.  Pointers and strides must allow 4-element vector access. */
+int pr_pool_accumulate(float *acc_dev, int32_t n_acc_rows, int32_t n_probers, int32_t slot, int32_t d_model,
+                       const void *act_dev, int32_t act_dtype, int32_t n_rows, int32_t n_tokens,
+                       int64_t row_stride, int64_t tok_stride, const int32_t *row_map_dev, pr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,7 @@ SIGNATURES = {
     "pr_index_aux_bytes": (c_sz, [c_vp, c_sz]),
     "pr_index_build_aux": (ctypes.c_int, [c_vp, c_vp, c_sz, c_vp]),
     "pr_index_aux_info": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i32), ctypes.POINTER(c_i64)]),
+    "pr_index_lean_info": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i32), ctypes.POINTER(c_i64)]),
     "pr_index_hot_info": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i32), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "pr_index_set_tuning": (ctypes.c_int, [c_vp, ctypes.POINTER(Tuning)]),
     "pr_index_get_tuning": (ctypes.c_int, [c_vp, ctypes.POINTER(Tuning)]),
@@ -54,6 +55,8 @@ SIGNATURES = {
     "pr_bm25_profile": (ctypes.c_int, [c_vp, ctypes.POINTER(c_f32), ctypes.POINTER(c_i32)]),
     "pr_topk_merge": (ctypes.c_int, [c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pr_prober_workspace_bytes": (c_sz, [c_i32, c_i32, c_i32, c_i32]),
+    "pr_pool_accumulate": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_i64, c_i64,
+                                          c_vp, c_vp]),
     "pr_prober_forward": (ctypes.c_int, [ctypes.POINTER(ProberSet), c_i32, c_vp, c_f32, c_i32, c_vp, c_vp, c_vp,
                                          c_vp, c_vp, c_vp, c_sz, c_vp]),
 }

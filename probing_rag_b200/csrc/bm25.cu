@@ -29,6 +29,7 @@
 #include "common.cuh"
 #include "bm25_warp.cuh"
 #include "bm25_flat.cuh"
+#include "bm25_lean.cuh"
 
 namespace {
 
@@ -495,6 +496,11 @@ struct pr_index {
     // largest weight per term (rank-safe term skipping, mode 7), also in the aux buffer
     const float *term_maxw;
     const float *row_q;   // [n_rows][2] weight levels ~1% / ~10% of a tabulated row's postings reach (planner cost model)
+    // cold stream of the lean kernel (bm25_lean.cuh, mode 8): every CSR posting as an (offset, weight) pair, in the
+    // aux buffer in front of the hot stream; lean_ok = it exists and the whole stream space fits 32-bit granule indices
+    const unsigned char *cold_stream;
+    uint32_t hot_base_g;
+    bool lean_ok;
 };
 
 namespace {
@@ -603,6 +609,22 @@ warp_fn_t pick_flat_fn(int nw, int E, bool skip)
     return pick_flat<8, false>(E);
 }
 
+template <int NW>
+warp_fn_t pick_lean(int E)
+{
+    if (E == 1) return prl::bm25_lean_kernel<NW, 1>;
+    if (E == 2) return prl::bm25_lean_kernel<NW, 2>;
+    return prl::bm25_lean_kernel<NW, 4>;
+}
+
+warp_fn_t pick_lean_fn(int nw, int E)
+{
+    if (nw == 4) return pick_lean<4>(E);
+    if (nw == 10) return pick_lean<10>(E);
+    if (nw == 12) return pick_lean<12>(E);
+    return pick_lean<8>(E);
+}
+
 int launch_merge(int E, dim3 grid, cudaStream_t st, const float *ps, const int32_t *pd, int C,
                  int64_t sq, int64_t sc, float *rs, int32_t *rd, float *rt, int B, int K, int fin,
                  float *os, int32_t *od, int base, int n_docs)
@@ -619,7 +641,7 @@ void default_tuning(pr_bm25_tuning_t *t)
     t->tile_docs = 24576;
     t->tiles_per_item = 4;
     t->threads = 512;
-    t->mode = 6;
+    t->mode = 8;
     t->min_items = 2048;
     t->cand_cap = 1024;
     t->subs_per_item = 24;
@@ -649,7 +671,7 @@ int check_tuning(const pr_bm25_tuning_t &t)
                      t.subs_per_item, t.docs_per_launch, t.warps_per_cta);
         return PR_EINVAL;
     }
-    if (t.tiles_per_item < 1 || t.mode < 1 || t.mode > 7 || t.min_items < 1 || t.cand_cap < 32) {
+    if (t.tiles_per_item < 1 || t.mode < 1 || t.mode > 8 || t.min_items < 1 || t.cand_cap < 32) {
         pr_set_error("bad tuning (tiles_per_item=%d mode=%d min_items=%d cand_cap=%d)",
                      t.tiles_per_item, t.mode, t.min_items, t.cand_cap);
         return PR_EINVAL;
@@ -729,6 +751,9 @@ extern "C" int pr_index_create(pr_index_t **out, int device, int64_t n_docs_glob
     ix->n_hot = 0;
     ix->hot_min_df = 0;
     ix->hot_stream_bytes = 0;
+    ix->cold_stream = nullptr;
+    ix->hot_base_g = 0;
+    ix->lean_ok = false;
     ix->term_maxw = nullptr;
     ix->row_q = nullptr;
     {   // lazily re-zeroed accumulators need every weight in [2^-30, 2^10] (bm25_warp.cuh)
@@ -758,7 +783,8 @@ extern "C" size_t pr_index_aux_bytes(const pr_index_t *index, size_t table_budge
     if (!index) return 0;
     // heavy_row[n_terms] + block counts + row_term/tp within the budget
     const size_t fixed = 2 * align_up((size_t)index->n_terms * 4, 256) + align_up(((size_t)index->n_terms / 1024 + 2) * 4, 256) + 256;
-    return fixed + align_up(table_budget_bytes, 256);
+    // + the cold stream of the lean kernel: 8 bytes per posting
+    return fixed + align_up(table_budget_bytes, 256) + align_up((size_t)index->nnz * 8 + 256, 256);
 }
 
 extern "C" int pr_index_build_aux(pr_index_t *index, void *aux_dev, size_t aux_bytes, pr_stream_t stream)
@@ -779,6 +805,14 @@ extern "C" int pr_index_build_aux(pr_index_t *index, void *aux_dev, size_t aux_b
     if (o > aux_bytes) {
         pr_set_error("pr_index_build_aux: aux buffer of %zu bytes, need at least %zu", aux_bytes, o);
         return PR_EWORKSPACE;
+    }
+    // the cold stream (8 bytes per posting) is carved first when the buffer was sized by pr_index_aux_bytes
+    // with a budget that leaves room for it; a smaller buffer simply has none (mode 8 then runs as mode 6)
+    const size_t cold_bytes = align_up((size_t)index->nnz * 8 + 256, 256);
+    unsigned char *cold = nullptr;
+    if (index->nnz > 0 && aux_bytes >= o + cold_bytes) {
+        cold = p + o;
+        o += cold_bytes;
     }
     // the boundary table gets a fifth of the table budget (at least 16 MB of it), the hot stream the rest
     const size_t budget = aux_bytes - o;
@@ -825,6 +859,16 @@ extern "C" int pr_index_build_aux(pr_index_t *index, void *aux_dev, size_t aux_b
     index->n_hot = 0;
     index->hot_min_df = 0;
     index->hot_stream_bytes = 0;
+    index->cold_stream = nullptr;
+    index->hot_base_g = 0;
+    index->lean_ok = false;
+    if (cold) {
+        prl::cold_fill_kernel<<<2368, 256, 0, st>>>(index->doc_ids, index->weights, index->nnz, (uint2 *)cold);
+        PR_CUDA_CHECK(cudaGetLastError());
+        PR_CUDA_CHECK(cudaStreamSynchronize(st));
+        index->cold_stream = cold;
+        index->lean_ok = (uint64_t)index->nnz + 64 < ((uint64_t)1 << 32);  // without a hot stream
+    }
 
     // ---- hot posting stream (bm25_hot.cuh) for the tabulated terms with >= kHotMinSeg postings
     // per sub-tile, as many of them as the rest of the buffer holds (threshold doubles until it fits)
@@ -870,6 +914,11 @@ extern "C" int pr_index_build_aux(pr_index_t *index, void *aux_dev, size_t aux_b
         index->n_hot = H;
         index->hot_min_df = hot_df;
         index->hot_stream_bytes = (int64_t)total * prh::kUnitBytes;
+        if (cold) {  // one granule space: cold stream, tables, hot stream
+            const uint64_t g0 = (uint64_t)(stream_dev - cold) >> 3;
+            index->hot_base_g = (uint32_t)g0;
+            index->lean_ok = g0 + (uint64_t)total * 32 + 64 < ((uint64_t)1 << 32);
+        }
         return PR_OK;
     }
 }
@@ -883,6 +932,17 @@ extern "C" int pr_index_hot_info(const pr_index_t *index, int32_t *n_hot, int64_
     *n_hot = index->n_hot;
     *min_df = index->hot_min_df;
     *stream_bytes = index->hot_stream_bytes;
+    return PR_OK;
+}
+
+extern "C" int pr_index_lean_info(const pr_index_t *index, int32_t *lean_ok, int64_t *cold_bytes)
+{
+    if (!index || !lean_ok || !cold_bytes) {
+        pr_set_error("pr_index_lean_info: null argument");
+        return PR_EINVAL;
+    }
+    *lean_ok = index->lean_ok ? 1 : 0;
+    *cold_bytes = index->cold_stream ? index->nnz * 8 : 0;
     return PR_OK;
 }
 
@@ -1024,13 +1084,14 @@ extern "C" int pr_bm25_topk(pr_index_t *index, int32_t n_queries, const int64_t 
     const int nw = warp_mode ? t.warps_per_cta : t.threads / 32;
     const int threads = nw * 32;
     const bool flat_mode = t.mode >= 5;
-    const size_t smem = flat_mode ? prf::flat_smem_bytes(nw)
+    const bool lean_mode = t.mode == 8 && index->lean_ok;  // mode 8 without a cold stream runs the flat kernel (mode 6)
+    const size_t smem = lean_mode ? prl::lean_smem_bytes(nw) : flat_mode ? prf::flat_smem_bytes(nw)
                                   : warp_mode ? prw::warp_smem_bytes(nw) : score_smem_bytes(t.tile_docs, t.cand_cap, nw, k);
     score_fn_t fn = nullptr;
     warp_fn_t wfn = nullptr;
     const void *kfn = nullptr;
     if (warp_mode) {
-        wfn = flat_mode ? pick_flat_fn(nw, E, t.mode == 7) : pick_warp_fn(nw, E, index->lazy_ok && t.lazy_zero == 1);
+        wfn = lean_mode ? pick_lean_fn(nw, E) : flat_mode ? pick_flat_fn(nw, E, t.mode == 7) : pick_warp_fn(nw, E, index->lazy_ok && t.lazy_zero == 1);
         kfn = (const void *)wfn;
     } else {
         fn = pick_score_fn(t.threads, E);
@@ -1075,6 +1136,8 @@ extern "C" int pr_bm25_topk(pr_index_t *index, int32_t n_queries, const int64_t 
     w.hot_of_row = index->hot_of_row;
     w.hot_off = index->hot_off;
     w.hot_stream = index->hot_stream;
+    w.stream_base = index->cold_stream;
+    w.hot_base_g = index->hot_base_g;
     w.term_maxw = index->term_maxw;
     w.plan_mask = plan_mask;
     w.plan_m = plan_m;
@@ -1118,7 +1181,7 @@ extern "C" int pr_bm25_topk(pr_index_t *index, int32_t n_queries, const int64_t 
             w.chunk0 = li * l.C;
             w.n_chunks_launch = Cl;
             w.counter = counters + li;
-            w.mode = li == 0 ? (flat_mode ? 5 : 3) : t.mode;  // the first launch has no running k-th score yet
+            w.mode = li == 0 ? (flat_mode ? 5 : 3) : (t.mode == 8 ? 6 : t.mode);  // the first launch has no running k-th score yet
             wfn<<<(unsigned)grid, threads, smem, st>>>(w);
         } else {
             a.chunk0 = li * l.C;

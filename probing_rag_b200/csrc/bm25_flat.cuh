@@ -651,9 +651,9 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_FLAT_CTAS : NW <= 8
                 b.d = ldg_stream_u4(p);
                 b.w = ldg_stream_f4(p + 512);
             } else if (kind == kStepNarrow) {
-                const unsigned char *p = a.hot_stream + (size_t)ds.x * prh::kUnitBytes + lane * 4;
+                const unsigned char *p = a.hot_stream + (size_t)ds.x * prh::kUnitBytes + lane * 8;  // interleaved (offset, weight) pairs
                 b.d.x = ldg_stream_u1(p);
-                b.w.x = ldg_stream_f1(p + 128);
+                b.w.x = ldg_stream_f1(p + 4);
             } else if (kind == kStepGen) {
                 const int64_t p = ((int64_t)(ds.y >> 8) << 32 | ds.x) + lane;
                 if (lane < (int)((ds.y >> 2) & 63u)) {

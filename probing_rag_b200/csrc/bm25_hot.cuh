@@ -9,7 +9,7 @@
 // (term, sub-tile) segment re-laid-out as a sequence of mask-free STEPS:
 //
 //   wide step   1 KB : [32 lanes x 4 tile byte-offsets u32][32 lanes x 4 weights f32]
-//   narrow step 256 B: [32 lanes x 1 tile byte-offset u32 ][32 lanes x 1 weight f32 ]
+//   narrow step 256 B: 32 lanes x (tile byte-offset u32, weight f32) pairs, interleaved
 //
 //   * offsets are pre-scaled byte offsets into the warp's tile (no masking / shifting per slot);
 //   * segments are padded to whole steps with (dummy word, +0.0f) slots, so there are no
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(256) hot_fill_kernel(const int64_t *indptr, co
         }
         for (int i = lane; i < n_narrow * 64; i += 32) {
             const int in_step = i & 63;
-            out[n_wide * 256 + i] = in_step < 32 ? (uint32_t)(kSub + in_step) * 4u : 0u;
+            out[n_wide * 256 + i] = (in_step & 1) ? 0u : (uint32_t)(kSub + (in_step >> 1)) * 4u;
         }
         // ---- bank histogram -> start of every bank in bank-sorted order
         const int64_t p0 = indptr[row_term[row]] + sb;
@@ -204,8 +204,8 @@ __global__ void __launch_bounds__(256) hot_fill_kernel(const int64_t *indptr, co
                 ow = (grp >> 2) * 256 + ln * 4 + (grp & 3);
                 ww = ow + 128;
             } else {
-                ow = n_wide * 256 + (grp - 4 * n_wide) * 64 + ln;
-                ww = ow + 32;
+                ow = n_wide * 256 + (grp - 4 * n_wide) * 64 + 2 * ln;
+                ww = ow + 1;
             }
             out[ow] = (uint32_t)(d & (kSub - 1)) * 4u;
             out[ww] = __float_as_uint(wt);

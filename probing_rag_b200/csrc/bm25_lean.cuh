@@ -1,0 +1,611 @@
+// Lean-step BM25 scoring kernel (tuning.mode 8): the flat-step design of bm25_flat.cuh -- one warp
+// owns a (query, document-range) work item and a private 2048-document fp32 score tile in shared
+// memory, applies the query's terms in query-token order (one rounded fp32 add per posting:
+// bit-identical to the reference's dense accumulator) and runs ONE loop over step descriptors with
+// the loads issued kPipe steps ahead -- with the per-step instruction overhead cut roughly in half.
+// ncu on the flat kernel (profiles/r01/v4_flat_kernel_ncu_summary.txt) showed ~60 warp
+// instructions per 128-slot step and ~50 per 32-slot step, most of them control: three step kinds
+// decoded by divergent-looking branches (BSSY/BSYNC pairs, BRA.DIV guards in front of every vote),
+// two descriptor lists with bounds checks, 64-bit address assembly for CSR steps, S2R
+// rematerialisation.  Here:
+//
+//   * ONE posting address space.  Next to the hot stream the index keeps a COLD stream: every CSR
+//     posting as an interleaved (pre-scaled tile byte offset, weight) pair, 8 bytes, at granule
+//     index = posting index.  Hot narrow units are interleaved pairs too.  A descriptor is
+//     (granule index u32, flags): address = base + 8 * (granule + lane [* 2]).  Two step shapes
+//     remain: WIDE (4 slots per lane, two 128-bit loads) and NARROW (one 64-bit load for the lanes
+//     below `cnt`; the others add +0.0f to their dummy word).  No-op and END steps are narrow steps
+//     with cnt = 0, so there is no third kind.
+//   * Every branch of the step loop is taken on a VOTED predicate or a REDUX-ed counter, which
+//     ptxas knows to be warp-uniform: no reconvergence barriers, no divergence guards.
+//   * The two descriptor lists become one 128-entry ring; each produced list is followed by kPipe
+//     no-op descriptors, so the look-ahead never needs a bounds check.
+//
+// Mode 7 (rank-safe term skipping) stays with the flat kernel.
+#pragma once
+
+#include "bm25_flat.cuh"
+
+#ifndef PR_LEAN_PIPE
+#define PR_LEAN_PIPE 3
+#endif
+#ifndef PR_LEAN_CTAS
+#define PR_LEAN_CTAS 3
+#endif
+
+namespace prl {
+
+using prw::kSub;
+using prw::kSubShift;
+using prw::WarpArgs;
+using prf::kScanLimit;
+using prf::kTileWords;
+using prf::lds_f32;
+using prf::lds_u2;
+using prf::ldg_stream_f4;
+using prf::ldg_stream_u4;
+using prf::sts_f32;
+
+constexpr int kRing = 128;    // step descriptors in the per-warp ring (two lists + the trailing no-ops)
+constexpr int kListCap = 60;  // longest list one producer call lays out
+constexpr int kPipe = PR_LEAN_PIPE;
+static_assert(2 * kListCap + kPipe <= kRing, "ring too small");
+static_assert(kListCap % kPipe == 0, "lists are whole rings of kPipe steps");
+
+// descriptor .y: bit 0 wide step, bit 1 end of sub-tile (sub-tile index in bits 31..8), bits 7..2 valid lanes of a narrow step
+enum : uint32_t { kFlagWide = 1, kFlagEnd = 2 };
+
+// rings first (the block is re-aligned to 1 KB inside the kernel so a ring slot is `base | offset`), then the tiles
+__host__ __device__ inline size_t lean_smem_bytes(int nw) { return (size_t)nw * (kTileWords * 4 + kRing * 8) + 1024; }
+
+struct StepBuf {
+    uint4 d;  // tile byte offsets (.x only: narrow)
+    float4 w;
+    uint32_t meta;
+    uint32_t wide;  // the wide flag
+};
+
+__device__ __forceinline__ uint2 ldg_stream_u2(const void *p)
+{
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void sts_u2(uint32_t a, uint32_t x, uint32_t y)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+// warp-uniform copy of a value all lanes agree on; REDUX writes a uniform register, so ptxas
+// treats everything derived from it (loop bounds, branch conditions) as convergent
+__device__ __forceinline__ int uni(int v) { return __reduce_max_sync(PR_FULL_MASK, v); }
+
+// cold stream: posting p of the CSR as (tile byte offset, weight bits)
+__global__ void __launch_bounds__(256) cold_fill_kernel(const int32_t *__restrict__ doc_ids, const float *__restrict__ weights,
+                                                        int64_t nnz, uint2 *__restrict__ cold)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += stride)
+        cold[p] = make_uint2((uint32_t)(doc_ids[p] & (kSub - 1)) * 4u, __float_as_uint(weights[p]));
+}
+
+template <int NW, int E>
+__global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8 ? PR_LEAN_CTAS : NW <= 12 ? 2 : 1))
+    bm25_lean_kernel(const WarpArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    asm volatile("" : "+r"(lane));  // opaque: kept in a register instead of being rematerialised by S2R in the step loop
+    unsigned char *smem_al = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
+    uint2 *desc = reinterpret_cast<uint2 *>(smem_al) + warp * kRing;
+    float *tile = reinterpret_cast<float *>(smem_al + (size_t)NW * kRing * 8) + warp * kTileWords;
+    float4 *tile4 = reinterpret_cast<float4 *>(tile);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t tile_sa = (uint32_t)__cvta_generic_to_shared(tile);
+    uint32_t desc_sa = (uint32_t)__cvta_generic_to_shared(desc);  // 1 KB aligned
+    asm volatile("" : "+r"(tile_sa), "+r"(desc_sa));
+    const uint32_t dummy_off = (uint32_t)(kSub + lane) * 4u;
+    const unsigned char *const sbase = a.stream_base;
+    const uint32_t hot_base_g = a.hot_base_g;
+
+#pragma unroll
+    for (int v = lane; v < kTileWords / 4; v += 32) tile4[v] = zero4;
+    __syncwarp();
+
+    const int K = a.K, C = a.n_chunks_launch, G = a.subs_per_item;
+    const int64_t n_items = (int64_t)a.n_queries * C;
+    const size_t tab_stride = (size_t)a.n_sub + 1;
+    WarpTopK<E> item;
+
+    auto slot = [&](int pos) -> uint32_t { return desc_sa | (((uint32_t)pos << 3) & (uint32_t)(kRing * 8 - 8)); };
+
+    while (true) {
+        int item_i = 0;
+        if (lane == 0) item_i = atomicAdd(a.counter, 1);
+        item_i = __shfl_sync(PR_FULL_MASK, item_i, 0);
+        if ((int64_t)item_i >= n_items) break;
+        const int q = item_i / C, c = item_i % C;
+        const int64_t qb = a.q_indptr[q];
+        const int nq = (int)(a.q_indptr[q + 1] - qb);
+        const float theta_run = a.run_theta[q];
+        const bool update_mode = theta_run > 0.f;
+        item.reset();
+        float thr = fmaxf(theta_run, PR_DENORM_MIN);  // warp-uniform filter for candidates
+        float iks = PR_SENT_SCORE;
+        int ikd = PR_SENT_DOC;
+        const int sub0 = (a.chunk0 + c) * G;
+        const int sub1 = min(sub0 + G, a.n_sub);
+        const bool single = nq <= 32;
+        float mx = 0.f;  // per lane: largest accumulator value written for the sub-tile being drained
+        float thr_push = update_mode ? thr : 0.f  /* no threshold yet: every sub-tile is scanned */;
+
+        // ---- per-lane description of one query term (lane j <-> term p0+j of the current pass)
+        // class: 2 = hot (steps from the hot stream, boundaries hot_off[t_row][g]), 1 = tabulated
+        // (cold stream, boundaries tp[t_row][g]), 0 = rare (cold stream, cursor), -1 = no term
+        int t_class = -1;
+        int64_t t_b0 = 0;                 // start of the term's posting list (classes 0, 1)
+        int32_t t_row = 0;                // row of hot_off / tp
+        uint32_t tb_cur = 0, tb_next = 0; // single pass, classes 1, 2: table entries g+1, g+2
+        // class 0: [t_pos, t_le) = postings not yet consumed inside the item's (single pass) or the
+        // sub-tile's (several passes) document range, relative to t_b0; t_nd = document at t_pos
+        int32_t t_pos = 0, t_le = 0, t_nd = 0x7fffffff;
+
+        auto load_info = [&](int p0, int np, int dlo, int dhi) {
+            t_class = -1;
+            t_b0 = 0;
+            t_row = 0;
+            t_pos = 0;
+            t_le = 0;
+            t_nd = 0x7fffffff;
+            int32_t df = 0;
+            if (lane < np) {
+                const int32_t t = a.q_terms[qb + p0 + lane];
+                if (t < 0 || t >= a.n_terms) {
+                    atomicOr(a.status, 1);
+                } else {
+                    t_b0 = a.indptr[t];
+                    df = (int32_t)(a.indptr[t + 1] - t_b0);
+                    const int row = a.heavy_row[t];
+                    t_class = row >= 0 ? 1 : 0;
+                    t_row = row;
+                    if (row >= 0 && a.hot_of_row) {
+                        const int h = a.hot_of_row[row];
+                        if (h >= 0) {
+                            t_class = 2;
+                            t_row = h;
+                        }
+                    }
+                }
+            }
+            const bool rare = t_class == 0 && df > 0;
+            unsigned sm = __ballot_sync(PR_FULL_MASK, rare);
+            while (sm) {  // locate [dlo, dhi) in the list by a warp-collective search
+                const int j = __ffs(sm) - 1;
+                sm &= sm - 1;
+                const int64_t b0 = __shfl_sync(PR_FULL_MASK, t_b0, j);
+                const int64_t e0 = b0 + __shfl_sync(PR_FULL_MASK, df, j);
+                const int64_t lo = pr_lower_bound_warp(a.doc_ids, b0, e0, dlo, lane);
+                int64_t lim = lo + (dhi - dlo);
+                if (lim > e0) lim = e0;
+                const int64_t hi = pr_lower_bound_warp(a.doc_ids, lo, lim, dhi, lane);
+                if (lane == j) {
+                    t_pos = (int32_t)(lo - b0);
+                    t_le = (int32_t)(hi - b0);
+                }
+            }
+            if (rare && t_pos < t_le) t_nd = __ldg(a.doc_ids + t_b0 + t_pos);
+        };
+
+        if (single && nq > 0) load_info(0, nq, sub0 << kSubShift, min(sub1 << kSubShift, a.n_docs));
+
+        // ---- producer: the next list of step descriptors of this item, in (sub-tile, pass, chunk) order
+        int it_g = nq > 0 ? sub0 : sub1, it_p0 = 0, it_w0 = 0;
+        bool it_touched = false;          // a step was emitted for sub-tile it_g
+        uint32_t seg_x = 0;               // per lane, for (it_g, it_p0): first table unit / posting (relative)
+        int32_t seg_len = 0;              // ... and how many
+
+        // this lane's step descriptors k in [k0, k1) of its current segment (seg_x, seg_len), from ring position `pos` on
+        auto write_steps = [&](int pos, int k0, int k1, int n_wide) {
+            if (t_class == 2) {
+#pragma unroll 1
+                for (int k = k0; k < k1; ++k, ++pos) {
+                    const bool wide = k < n_wide;
+                    const uint32_t unit = wide ? seg_x + 4u * (uint32_t)k : seg_x + 3u * (uint32_t)n_wide + (uint32_t)k;
+                    sts_u2(slot(pos), hot_base_g + unit * 32u, wide ? (uint32_t)kFlagWide : (32u << 2));
+                }
+            } else {
+                uint32_t p = (uint32_t)t_b0 + seg_x + 32u * (uint32_t)k0;  // granule = posting index (< 2^32: checked by the host)
+                int left = seg_len - 32 * k0;
+#pragma unroll 1
+                for (int k = k0; k < k1; ++k, ++pos, p += 32u, left -= 32) sts_u2(slot(pos), p, (uint32_t)min(32, left) << 2);
+            }
+        };
+        // what follows every list: kPipe no-ops for the look-ahead of the consumer (overwritten by the next list)
+        auto finish_list = [&](int pos) {
+            if (lane < kPipe) sts_u2(slot(pos + lane), 0u, 0u);
+            __syncwarp();
+        };
+
+        auto produce = [&](const int tl) -> int {
+            while (it_g < sub1) {
+                const int g = it_g;
+                if (it_w0 == 0) {  // new (sub-tile, pass): what each term has inside this sub-tile
+                    const int sub_lo = g << kSubShift;
+                    const int sub_hi = sub_lo + min(kSub, a.n_docs - sub_lo);
+                    if (!single) load_info(it_p0, min(32, nq - it_p0), sub_lo, sub_hi);
+                    uint32_t sb = 0, se = 0;
+                    int32_t scan_e = 0;
+                    bool unresolved = false;
+                    if (t_class >= 1) {
+                        const uint32_t *tab = (t_class == 2 ? a.hot_off : a.tp) + (size_t)t_row * tab_stride + g;
+                        if (single && g > sub0) {  // carried from the previous sub-tile / prefetched
+                            sb = tb_cur;
+                            se = tb_next;
+                        } else {
+                            sb = __ldg(tab);
+                            se = __ldg(tab + 1);
+                        }
+                        if (single) {  // entry g+2, needed by the next sub-tile: load it now
+                            tb_cur = se;
+                            if (g + 2 <= a.n_sub) tb_next = __ldg(tab + 2);
+                        }
+                    } else if (t_class == 0) {
+                        if (!single) {
+                            sb = (uint32_t)t_pos;  // located for exactly this sub-tile
+                            se = (uint32_t)t_le;
+                        } else if (t_nd < sub_hi) {  // cursor: the term has a posting in this sub-tile
+                            sb = (uint32_t)t_pos;
+                            scan_e = t_pos + 1;
+                            int probe = 0x7fffffff;
+                            unresolved = true;
+#pragma unroll 1
+                            for (int it = 0; it < kScanLimit; ++it) {
+                                probe = scan_e < t_le ? __ldg(a.doc_ids + t_b0 + scan_e) : 0x7fffffff;
+                                if (probe >= sub_hi) {
+                                    unresolved = false;
+                                    break;
+                                }
+                                ++scan_e;
+                            }
+                            if (!unresolved) {
+                                se = (uint32_t)scan_e;
+                                t_pos = scan_e;
+                                t_nd = probe;
+                            }
+                        }
+                    }
+                    unsigned um = __ballot_sync(PR_FULL_MASK, unresolved);
+                    while (um) {  // clustered rare term: finish with a warp-collective search
+                        const int j = __ffs(um) - 1;
+                        um &= um - 1;
+                        const int64_t b0 = __shfl_sync(PR_FULL_MASK, t_b0, j);
+                        const int64_t from = b0 + __shfl_sync(PR_FULL_MASK, scan_e, j);
+                        const int64_t lim = b0 + __shfl_sync(PR_FULL_MASK, t_le, j);
+                        const int64_t hi = pr_lower_bound_warp(a.doc_ids, from, lim, sub_hi, lane);
+                        if (lane == j) {
+                            se = (uint32_t)(hi - b0);
+                            t_pos = (int32_t)se;
+                        }
+                    }
+                    if (unresolved) t_nd = t_pos < t_le ? __ldg(a.doc_ids + t_b0 + t_pos) : 0x7fffffff;
+                    seg_x = sb;
+                    seg_len = (int32_t)(se - sb);
+                }
+                // ---- steps of this (sub-tile, pass), laid out in term order
+                int n_wide = 0, n = 0;
+                if (t_class == 2) {
+                    n_wide = seg_len >> 2;
+                    n = n_wide + (seg_len & 3);
+                } else if (t_class >= 0) {
+                    n = (seg_len + 31) >> 5;
+                }
+                int incl = n;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(PR_FULL_MASK, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int S = __shfl_sync(PR_FULL_MASK, incl, 31);
+                const int pre = incl - n;
+                const bool last_pass = it_p0 + 32 >= nq;
+                it_touched = it_touched || S > 0;
+                const int w0 = it_w0;
+                const int chunk = min(S - w0, kListCap - kPipe);
+                const bool fin = w0 + chunk >= S;
+                const bool end = fin && last_pass && it_touched;
+                // advance the iterator
+                if (!fin) {
+                    it_w0 = w0 + chunk;
+                } else {
+                    it_w0 = 0;
+                    if (last_pass) {
+                        it_g = g + 1;
+                        it_p0 = 0;
+                        it_touched = false;
+                    } else {
+                        it_p0 += 32;
+                    }
+                }
+                if (chunk == 0 && !end) continue;  // nothing in this pass / untouched sub-tile
+                // ---- this lane's entries k in [k0, k1) -> list positions pre + k - w0
+                write_steps(tl + pre + max(0, w0 - pre) - w0, max(0, w0 - pre), min(n, w0 + chunk - pre), n_wide);
+                // ---- no-ops up to a multiple of kPipe; an END step always sits in the last ring slot
+                int len = chunk;
+                const int pad = (kPipe - ((len + (end ? 1 : 0)) % kPipe)) % kPipe;
+                if (lane < pad) sts_u2(slot(tl + len + lane), 0u, 0u);
+                len += pad;
+                if (end) {
+                    if (lane == 0) sts_u2(slot(tl + len), 0u, (uint32_t)kFlagEnd | ((uint32_t)g << 8));
+                    ++len;
+                }
+                finish_list(tl + len);
+                return len;
+            }
+            finish_list(tl);
+            return 0;
+        };
+
+        // ---- fast producer: queries of <= 16 terms whose rare terms have <= 4 postings in the item's range
+        // (almost every round-0 query).  The lanes are re-mapped to (sub-tile slot s, term j) = (lane / TPL,
+        // lane % TPL), TPL = 8 or 16, so ONE pass of table look-ups, prefix sums and descriptor stores lays out
+        // 32 / TPL consecutive sub-tiles; a rare term's few documents sit in registers (tb_cur, tb_next, t_nd,
+        // t_le re-used), so there is no cursor.  A sub-tile whose steps overflow the list is cut into chunks.
+        const int tpl_shift = nq <= 8 ? 3 : 4;
+        const bool fast = single && nq > 0 && nq <= 16 && !__any_sync(PR_FULL_MASK, t_class == 0 && t_le - t_pos > 4);
+        if (fast) {
+            const int j = lane & ((1 << tpl_shift) - 1);
+            const int c_ = __shfl_sync(PR_FULL_MASK, t_class, j), row_ = __shfl_sync(PR_FULL_MASK, t_row, j);
+            const int pos_ = __shfl_sync(PR_FULL_MASK, t_pos, j), le_ = __shfl_sync(PR_FULL_MASK, t_le, j);
+            const int64_t b0_ = __shfl_sync(PR_FULL_MASK, t_b0, j);
+            t_class = c_;
+            t_row = row_;
+            t_b0 = b0_;
+            t_pos = pos_;
+            int dd[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+            if (c_ == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (pos_ + i < le_) dd[i] = __ldg(a.doc_ids + b0_ + pos_ + i);
+            }
+            tb_cur = (uint32_t)dd[0];
+            tb_next = (uint32_t)dd[1];
+            t_nd = dd[2];
+            t_le = dd[3];
+        }
+
+        auto produce_fast = [&](const int tl) -> int {
+            const int NS = 32 >> tpl_shift, TPL = 1 << tpl_shift;
+            const int s = lane >> tpl_shift, j = lane & (TPL - 1);
+            while (it_g < sub1) {
+                const int g0 = it_g, g = g0 + s;
+                if (it_w0 == 0) {  // what each term has inside each of the NS sub-tiles
+                    uint32_t sb = 0, se = 0;
+                    if (g < sub1) {
+                        if (t_class >= 1) {
+                            const uint32_t *tab = (t_class == 2 ? a.hot_off : a.tp) + (size_t)t_row * tab_stride + g;
+                            sb = __ldg(tab);
+                            se = __ldg(tab + 1);
+                        } else if (t_class == 0) {
+                            const int lo = g << kSubShift, hi = a.n_docs - lo > kSub ? lo + kSub : a.n_docs;
+                            const int d0 = (int)tb_cur, d1 = (int)tb_next, d2 = t_nd, d3 = t_le;
+                            sb = (uint32_t)(t_pos + (d0 < lo) + (d1 < lo) + (d2 < lo) + (d3 < lo));
+                            se = (uint32_t)(t_pos + (d0 < hi) + (d1 < hi) + (d2 < hi) + (d3 < hi));
+                        }
+                    }
+                    seg_x = sb;
+                    seg_len = (int32_t)(se - sb);
+                }
+                int n_wide = 0, n = 0;
+                if (it_w0 == 0 || s == 0) {  // a chunked sub-tile continues with slot 0 only
+                    if (t_class == 2) {
+                        n_wide = seg_len >> 2;
+                        n = n_wide + (seg_len & 3);
+                    } else if (t_class >= 0) {
+                        n = (seg_len + 31) >> 5;
+                    }
+                }
+                if (!__any_sync(PR_FULL_MASK, n > 0)) {  // nothing in these sub-tiles
+                    it_g = g0 + NS;
+                    continue;
+                }
+                int incl = n;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(PR_FULL_MASK, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                int e_prev = __shfl_sync(PR_FULL_MASK, incl, max((s << tpl_shift) - 1, 0));
+                if (s == 0) e_prev = 0;
+                const int pre = incl - n - e_prev;  // steps of this lane's sub-tile before its own
+                // ---- lay the sub-tiles out one after the other: steps, no-ops up to the last ring slot, END
+                int base = 0, my_base = -1, my_t = 0, my_total = 0, ns_eff = 0, prev_e = 0, t0 = 0;
+                bool chunked = it_w0 > 0;
+                for (int ss = 0; ss < NS && !chunked; ++ss) {
+                    const int e = __shfl_sync(PR_FULL_MASK, incl, (ss << tpl_shift) + TPL - 1);
+                    const int t = e - prev_e;
+                    prev_e = e;
+                    if (ss == 0) t0 = t;
+                    if (t > 0) {
+                        const int total = (t + kPipe) / kPipe * kPipe;  // t steps + END, rounded up to whole rings
+                        if (base + total > kListCap) {
+                            chunked = ss == 0;
+                            break;
+                        }
+                        if (ss == s) {
+                            my_base = base;
+                            my_t = t;
+                            my_total = total;
+                        }
+                        base += total;
+                    }
+                    ns_eff = ss + 1;
+                }
+                if (!chunked) {
+                    it_g = g0 + ns_eff;
+                    if (base == 0) continue;  // the first non-empty sub-tile did not fit behind empty ones: next round
+                    if (my_base >= 0) {
+                        write_steps(tl + my_base + pre, 0, n, n_wide);
+                        const int pad = my_total - my_t - 1;
+                        if (j < pad) sts_u2(slot(tl + my_base + my_t + j), 0u, 0u);
+                        if (j == TPL - 1) sts_u2(slot(tl + my_base + my_total - 1), 0u, (uint32_t)kFlagEnd | ((uint32_t)g << 8));
+                    }
+                    finish_list(tl + base);
+                    return base;
+                }
+                // ---- one long sub-tile (g0), a chunk of its steps per call
+                if (it_w0 > 0) t0 = __shfl_sync(PR_FULL_MASK, incl, TPL - 1);
+                const int w0 = it_w0;
+                const int chunk = min(t0 - w0, kListCap - kPipe);
+                const bool fin = w0 + chunk >= t0;
+                if (!fin) {
+                    it_w0 = w0 + chunk;
+                } else {
+                    it_w0 = 0;
+                    it_g = g0 + 1;
+                }
+                if (s == 0) write_steps(tl + pre + max(0, w0 - pre) - w0, max(0, w0 - pre), min(n, w0 + chunk - pre), n_wide);
+                int len = chunk;
+                const int pad = (kPipe - ((len + (fin ? 1 : 0)) % kPipe)) % kPipe;
+                if (lane < pad) sts_u2(slot(tl + len + lane), 0u, 0u);
+                len += pad;
+                if (fin) {
+                    if (lane == 0) sts_u2(slot(tl + len), 0u, (uint32_t)kFlagEnd | ((uint32_t)g0 << 8));
+                    ++len;
+                }
+                finish_list(tl + len);
+                return len;
+            }
+            finish_list(tl);
+            return 0;
+        };
+
+        StepBuf buf[kPipe];
+        auto issue = [&](const int pos, StepBuf &b) {
+            const uint2 ds = lds_u2(slot(pos));
+            b.meta = ds.y;
+            b.wide = ds.y & kFlagWide;  // the same word in every lane: a uniform branch, cheaper than a vote + guard
+            if (b.wide) {
+                const unsigned char *p = sbase + ((size_t)(ds.x + 2u * (uint32_t)lane) << 3);
+                b.d = ldg_stream_u4(p);
+                b.w = ldg_stream_f4(p + 512);
+            } else {
+                // lanes at or past `cnt` keep (dummy word, +0.0f).  Two 32-bit loads, not one 64-bit load: a register
+                // pair would not line up with the wide step's two quads and ptxas would copy the loaded words
+                // right behind the load -- a full L2 latency stall per step (ncu, first version of this kernel)
+                uint32_t vx = dummy_off, vy = 0u;
+                if ((uint32_t)lane < ((ds.y >> 2) & 63u)) {
+                    const unsigned char *p = sbase + ((size_t)(ds.x + (uint32_t)lane) << 3);
+                    vx = prf::ldg_stream_u1(p);
+                    vy = prf::ldg_stream_u1(p + 4);
+                }
+                b.d.x = vx;
+                b.w.x = __uint_as_float(vy);
+            }
+        };
+        auto process = [&](const StepBuf &b, const bool may_end) {
+            // no warp barrier between steps: the warp is converged here (every branch of the loop is warp-uniform) and
+            // the shared-memory pipe runs one warp's instructions in order, so a step's stores land before the next
+            // step's loads; the asm statements carry "memory" clobbers, so the compiler keeps the order too
+            if (b.wide) {
+                const uint32_t oo[4] = {b.d.x, b.d.y, b.d.z, b.d.w};
+                const float ww[4] = {b.w.x, b.w.y, b.w.z, b.w.w};
+                float v[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) v[x] = lds_f32(tile_sa + oo[x]);
+#pragma unroll
+                for (int x = 0; x < 4; ++x) v[x] += ww[x];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) sts_f32(tile_sa + oo[x], v[x]);
+                mx = fmaxf(fmaxf(mx, v[0]), fmaxf(fmaxf(v[1], v[2]), v[3]));
+                return;
+            }
+            {
+                const uint32_t o = b.d.x;
+                const float v = lds_f32(tile_sa + o) + b.w.x;
+                sts_f32(tile_sa + o, v);
+                mx = fmaxf(mx, v);
+            }
+            if (may_end && __any_sync(PR_FULL_MASK, (b.meta & kFlagEnd) != 0u)) {
+                // ---- select from the finished sub-tile (padding slots only ever hold +0.0f) and re-zero it
+                const int g_end = (int)(b.meta >> 8);
+                const int base_doc = (g_end << kSubShift) + a.doc_id_base;
+                auto consider = [&](float bs, int off) {  // warp-uniform arguments, exact score
+                    const int bd = base_doc + off;
+                    if (bs >= thr && bs > theta_run && pr_beats(bs, bd, iks, ikd)) {
+                        item.insert(bs, bd, lane);
+                        item.kth(K, iks, ikd);
+                        thr = fmaxf(thr, iks);
+                    }
+                };
+                // threshold-on-update: scores only grow and weights are >= 0, so a document can enter the list only if
+                // one of its updates reached the running k-th score; that happens in well under 1% of the sub-tiles
+                // once a threshold exists, all the others are just re-zeroed
+                if (!__any_sync(PR_FULL_MASK, mx >= thr_push)) {
+#pragma unroll
+                    for (int vv = lane; vv < kSub / 4; vv += 32) tile4[vv] = zero4;
+                } else {
+                    const float thr_sel = thr;  // fixed while this sub-tile is selected from
+#pragma unroll 4
+                    for (int vv = lane; vv < kSub / 4; vv += 32) {
+                        const float4 xb = tile4[vv];
+                        tile4[vv] = zero4;
+                        const float xs[4] = {xb.x, xb.y, xb.z, xb.w};
+                        const bool any = (xs[0] >= thr_sel) || (xs[1] >= thr_sel) || (xs[2] >= thr_sel) || (xs[3] >= thr_sel);
+                        if (__any_sync(PR_FULL_MASK, any)) {
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc) {
+                                unsigned mm = __ballot_sync(PR_FULL_MASK, xs[cc] >= thr_sel);
+                                while (mm) {
+                                    const int l = __ffs(mm) - 1;
+                                    mm &= mm - 1;
+                                    consider(__shfl_sync(PR_FULL_MASK, xs[cc], l), 4 * (vv - lane + l) + cc);
+                                }
+                            }
+                        }
+                    }
+                }
+                mx = 0.f;
+                thr_push = update_mode ? thr : 0.f  /* no threshold yet: every sub-tile is scanned */;
+                __syncwarp();
+            }
+        };
+
+        // ---- consumer: drain the list produced one round earlier while the next one is already in the ring, so the
+        // look-ahead never runs dry.  hd = ring position of the next step to process, tl = end of what is produced.
+        int hd = 0, tl = 0, n_cur = 0;
+        bool first = true;
+        while (true) {
+            const int n_next = uni(fast ? produce_fast(tl) : produce(tl));
+            if (first) {
+                first = false;
+#pragma unroll
+                for (int d = 0; d < kPipe; ++d) issue(d, buf[d]);
+            }
+#pragma unroll 1
+            for (int s0 = 0; s0 < n_cur; s0 += kPipe) {
+#pragma unroll
+                for (int d = 0; d < kPipe; ++d) {
+                    process(buf[d], d == kPipe - 1);
+                    issue(hd + s0 + d + kPipe, buf[d]);
+                }
+            }
+            hd += n_cur;
+            tl += n_next;
+            n_cur = n_next;
+            if (n_cur == 0) break;
+        }
+
+        float *ps = a.part_s + ((size_t)q * C + c) * K;
+        int32_t *pdst = a.part_d + ((size_t)q * C + c) * K;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int i = e * 32 + lane;
+            if (i < K) {
+                ps[i] = item.s[e];
+                pdst[i] = item.d[e];
+            }
+        }
+    }
+}
+
+}  // namespace prl

@@ -45,6 +45,8 @@ struct WarpArgs {
     const int32_t *__restrict__ hot_of_row; // [n_rows] row of `hot_off`, or -1 (null: no hot stream)
     const uint32_t *__restrict__ hot_off;   // [n_hot][n_sub+1] 256-byte units of the hot stream before (row, sub-tile)
     const unsigned char *__restrict__ hot_stream;
+    const unsigned char *__restrict__ stream_base;  // lean kernel: cold stream (8-byte granule p = CSR posting p), hot stream behind it
+    uint32_t hot_base_g;                    // granule index of the hot stream's first byte relative to stream_base
     const float *__restrict__ term_maxw;    // [n_terms] largest weight of the term's list (mode 7), or null
     const uint32_t *__restrict__ plan_mask; // [n_queries] mode 7: bit j = term j of the query is skipped
     const float *__restrict__ plan_m;       // [n_queries] mode 7: upper bound of what the skipped terms add to a document

@@ -210,8 +210,11 @@ class BM25Index:
         n_hot, hot_df, hot_bytes = ctypes.c_int32(), ctypes.c_int64(), ctypes.c_int64()
         _lib.check(_lib.lib().pr_index_hot_info(self._handle, ctypes.byref(n_hot), ctypes.byref(hot_df),
                                                  ctypes.byref(hot_bytes)))
+        lean_ok, cold_bytes = ctypes.c_int32(), ctypes.c_int64()
+        _lib.check(_lib.lib().pr_index_lean_info(self._handle, ctypes.byref(lean_ok), ctypes.byref(cold_bytes)))
         return {"tp_rows": int(rows.value), "tp_min_df": int(min_df.value), "aux_bytes": int(self._aux.numel()),
-                "hot_rows": int(n_hot.value), "hot_min_df": int(hot_df.value), "hot_stream_bytes": int(hot_bytes.value)}
+                "hot_rows": int(n_hot.value), "hot_min_df": int(hot_df.value), "hot_stream_bytes": int(hot_bytes.value),
+                "lean_ok": bool(lean_ok.value), "cold_stream_bytes": int(cold_bytes.value)}
 
     @property
     def last_launches(self) -> int:

@@ -33,6 +33,10 @@ TUNINGS = [
     dict(mode=5, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304),
     dict(mode=6, subs_per_item=1, warps_per_cta=4, docs_per_launch=2048, min_items=1),
     dict(mode=6, subs_per_item=5, warps_per_cta=12, docs_per_launch=1000000, min_items=100000),
+    dict(mode=8, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304),                  # lean-step kernel (default)
+    dict(mode=8, subs_per_item=1, warps_per_cta=4, docs_per_launch=2048, min_items=1),
+    dict(mode=8, subs_per_item=5, warps_per_cta=12, docs_per_launch=1000000, min_items=100000),
+    dict(mode=8, subs_per_item=3, warps_per_cta=10, docs_per_launch=20000, min_items=2048),
     dict(mode=7, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304),                  # + rank-safe term skipping
     dict(mode=7, subs_per_item=4, warps_per_cta=8, docs_per_launch=8192),                    # many launches: skipping from launch 2 on
     dict(mode=7, subs_per_item=1, warps_per_cta=4, docs_per_launch=2048, min_items=1),
@@ -96,6 +100,8 @@ def test_depth_sweep(small_corpus, corpus_gpu, k):
                 dict(mode=3, subs_per_item=3, warps_per_cta=8, docs_per_launch=20000, min_items=2048),
                 dict(mode=6, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
                 dict(mode=5, subs_per_item=3, warps_per_cta=12, docs_per_launch=20000, min_items=2048),
+                dict(mode=8, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
+                dict(mode=8, subs_per_item=3, warps_per_cta=12, docs_per_launch=20000, min_items=2048),
                 dict(mode=7, subs_per_item=3, warps_per_cta=8, docs_per_launch=10000, min_items=2048)):
         corpus_gpu.set_tuning(**tun)
         gs, gd = run_gpu(corpus_gpu, qi, qt, k)
@@ -110,6 +116,8 @@ def test_small_batches(small_corpus, corpus_gpu, nq):
     for tun in (dict(threads=512, tile_docs=24576, tiles_per_item=4, mode=2, min_items=2048, cand_cap=1024),
                 dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
                 dict(mode=6, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
+                dict(mode=8, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
+                dict(mode=8, subs_per_item=2, warps_per_cta=8, docs_per_launch=8192, min_items=2048),
                 dict(mode=7, subs_per_item=2, warps_per_cta=8, docs_per_launch=8192, min_items=2048)):
         corpus_gpu.set_tuning(**tun)
         gs, gd = run_gpu(corpus_gpu, qi, qt, 10)
@@ -123,7 +131,7 @@ def test_long_transcript_queries(small_corpus, corpus_gpu):
     qi, qt = synth.queries_np(48, small_corpus["vocab"], idx["df"], kind="later")
     assert np.diff(qi).max() > 256
     os_, od = co.retrieve_batch(idx, qi, qt, 10, n_threads=8)
-    for mode in (1, 2, 3, 4, 5, 6, 7):
+    for mode in (1, 2, 3, 4, 5, 6, 7, 8):
         corpus_gpu.set_tuning(threads=512, tile_docs=24576, tiles_per_item=2, mode=mode, min_items=2048,
                               subs_per_item=4, warps_per_cta=8, docs_per_launch=98304 if mode < 7 else 16384)
         gs, gd = run_gpu(corpus_gpu, qi, qt, 10)
@@ -202,6 +210,8 @@ def test_tie_heavy_corpus():
                     dict(mode=6, subs_per_item=2, warps_per_cta=4, docs_per_launch=4096, min_items=1),
                     dict(mode=5, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=100000),
                     dict(mode=6, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
+                    dict(mode=8, subs_per_item=2, warps_per_cta=4, docs_per_launch=4096, min_items=1),
+                    dict(mode=8, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
                     dict(mode=7, subs_per_item=2, warps_per_cta=4, docs_per_launch=4096, min_items=1),
                     dict(mode=7, subs_per_item=3, warps_per_cta=8, docs_per_launch=8192, min_items=2048)):
             gi.set_tuning(**dict(dict(lazy_zero=1), **tun))
@@ -209,7 +219,7 @@ def test_tie_heavy_corpus():
             assert_parity(gs, gd, os_, od)
 
 
-@pytest.mark.parametrize("mode", [4, 6])
+@pytest.mark.parametrize("mode", [4, 6, 8])
 def test_without_boundary_tables_every_term_takes_the_cursor_path(small_corpus, mode):
     """aux budget 0 -> no term is tabulated: the head terms (thousands of postings per sub-tile,
     clustered far beyond the lane-local scan limit) go through the rare-term cursor + warp search."""

@@ -135,3 +135,90 @@ def test_config4_prober_gated_bm25(small_corpus):
     assert 0 < len(sel) < nq
     os_, od = co.retrieve_batch(idx, qi, qt, 10, n_threads=8)
     assert np.array_equal(ids.cpu().numpy(), od[sel]) and np.array_equal(scores.cpu().numpy(), os_[sel])
+
+
+# ---- on-device hidden-state pooling vs the reference's hook + concat + sum ------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_pooler_matches_reference_cache_concat_sum(dtype):
+    """exp_rag.py:317-321 + 385-386: per layer, cache every forward call's activations on the host, drop
+    the prefill entry, concat over tokens, sum.  The pooler adds on the device instead."""
+    from functools import partial
+    from probing_rag_b200.pooling import HiddenStatePooler
+    g = torch.Generator().manual_seed(11)
+    layers = [f"blocks.{l}.hook_resid_post" for l in po.PROBE_LAYERS]
+    B, d = 5, po.D_MODEL
+    pooler = HiddenStatePooler(B, layers, d)
+    for gen in range(2):                         # two generations: reset() in between like `cache = {}`
+        pooler.reset()
+        cache = {}
+        steps = [7] + [1] * (13 + gen)           # prefill of 7 tokens, then one token per decode step
+        for T in steps:
+            for name in layers:
+                act = (torch.randn(B, T, d, generator=g) * 3).to(dtype).cuda()
+                out = partial(pooler.hook_fn, layer=name)(act, None)
+                assert out is act
+                cache.setdefault(name, []).append(act.detach().cpu())
+        ref = torch.stack([po.pool_hidden_states([e.float() for e in cache[name]]) for name in layers], dim=1)
+        torch.cuda.synchronize()
+        got = pooler.X.cpu()
+        assert got.shape == (B, len(layers), d)
+        # same addends, fp32 accumulation; only the summation order over <= 14 tokens may differ
+        assert torch.allclose(got, ref, rtol=1e-5, atol=1e-4), (got - ref).abs().max()
+        assert pooler.calls(layers[0]) == len(steps)
+
+
+@pytest.mark.gpu
+def test_pooler_row_map_strides_and_errors():
+    from probing_rag_b200.pooling import HiddenStatePooler
+    g = torch.Generator().manual_seed(5)
+    pooler = HiddenStatePooler(6, ["a", "b"], 256)
+    big = torch.randn(4, 9, 512, generator=g).cuda()
+    view = big[:, 2:7, 128:384]                  # strided rows / tokens, offset features
+    rm = torch.tensor([5, -1, 0, 2], dtype=torch.int32)
+    pooler.add("b", view, row_map=rm)
+    pooler.add("b", view, row_map=rm)
+    torch.cuda.synchronize()
+    want = torch.zeros(6, 2, 256)
+    s = view.cpu().sum(dim=1)
+    for r, dst in enumerate(rm.tolist()):
+        if dst >= 0:
+            want[dst, 1] = s[r] + s[r]
+    assert torch.allclose(pooler.X.cpu(), want, rtol=1e-5, atol=1e-5)
+    with pytest.raises(ValueError):
+        pooler.add("a", torch.zeros(7, 1, 256, device="cuda"))      # more rows than the accumulator
+    with pytest.raises(ValueError):
+        pooler.add("a", torch.zeros(2, 1, 128, device="cuda"))      # wrong d_model
+    with pytest.raises(KeyError):
+        pooler.add("c", torch.zeros(2, 1, 256, device="cuda"))
+
+
+@pytest.mark.gpu
+def test_pooled_states_feed_the_gate_like_the_reference_loop():
+    """hooks -> pooled X -> six probers -> gate, against the oracle chain on the host (exp_rag.py:381-415)."""
+    from probing_rag_b200.pooling import HiddenStatePooler
+    from probing_rag_b200.prober import ProberGate
+    g = torch.Generator().manual_seed(2)
+    layers = list(po.PROBE_LAYERS)
+    probers = []
+    for layer in layers:
+        p = po.OracleImprovedProbe(po.D_MODEL, po.N_CLASSES)
+        p.load_state_dict(po.make_prober_state(layer))
+        probers.append(p.eval())
+    B = 64
+    pooler = HiddenStatePooler(B, layers, po.D_MODEL)
+    pooler.reset()
+    cache = {l: [] for l in layers}
+    for T in [5] + [1] * 20:
+        for l in layers:
+            act = torch.randn(B, T, po.D_MODEL, generator=g) * 4
+            pooler.hook_fn(act.cuda(), None, layer=l)
+            cache[l].append(act)
+    x_ref = torch.stack([po.pool_hidden_states(cache[l]) for l in layers], dim=1)
+    ref_logits = po.prober_logits(probers, x_ref)
+    psum_ref, ret_ref = po.gate(ref_logits, 0.0, 0)
+    out = ProberGate([p.state_dict() for p in probers], device="cuda")(pooler.X, want_logits=True)
+    err = (torch.softmax(out.logits.cpu(), -1) - torch.softmax(ref_logits, -1)).abs().max().item()
+    assert err < 1e-3, err                        # north-star tolerance for prober probabilities
+    margin = (psum_ref[:, 0] - psum_ref[:, 1]).abs()
+    assert bool(((out.retrieve.cpu() == ret_ref) | (margin < 2e-3)).all())

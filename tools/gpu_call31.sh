@@ -1,0 +1,4 @@
+#!/bin/bash
+# ncu --set full of the lean kernel (mode 8) at full size, launch in the middle of a step
+mkdir -p gpurun_out
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:bm25_lean -s 100 -c 1 -o gpurun_out/prof_lean_c31 python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_lean_c31.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/ncu_lean_c31.log | cut -c1-300

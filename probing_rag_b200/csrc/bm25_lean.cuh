@@ -52,8 +52,10 @@ constexpr int kPipe = PR_LEAN_PIPE;
 static_assert(2 * kListCap + kPipe <= kRing, "ring too small");
 static_assert(kListCap % kPipe == 0, "lists are whole rings of kPipe steps");
 
-// descriptor .y: bit 0 wide step, bit 1 end of sub-tile (sub-tile index in bits 31..8), bits 7..2 valid lanes of a narrow step
-enum : uint32_t { kFlagWide = 1, kFlagEnd = 2 };
+// descriptor .y: bit 0 wide step, bit 1 end of sub-tile (sub-tile index in bits 31..9), bit 2 last step of its list,
+// bits 8..3 valid lanes of a narrow step
+enum : uint32_t { kFlagWide = 1, kFlagEnd = 2, kFlagLast = 4 };  // kFlagLast: last step of a produced list
+constexpr int kCntShift = 3, kSubIdxShift = 9;
 
 // rings first (the block is re-aligned to 1 KB inside the kernel so a ring slot is `base | offset`), then the tiles
 __host__ __device__ inline size_t lean_smem_bytes(int nw) { return (size_t)nw * (kTileWords * 4 + kRing * 8) + 1024; }
@@ -62,7 +64,6 @@ struct StepBuf {
     uint4 d;  // tile byte offsets (.x only: narrow)
     float4 w;
     uint32_t meta;
-    uint32_t wide;  // the wide flag
 };
 
 __device__ __forceinline__ uint2 ldg_stream_u2(const void *p)
@@ -211,18 +212,27 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                 for (int k = k0; k < k1; ++k, ++pos) {
                     const bool wide = k < n_wide;
                     const uint32_t unit = wide ? seg_x + 4u * (uint32_t)k : seg_x + 3u * (uint32_t)n_wide + (uint32_t)k;
-                    sts_u2(slot(pos), hot_base_g + unit * 32u, wide ? (uint32_t)kFlagWide : (32u << 2));
+                    sts_u2(slot(pos), hot_base_g + unit * 32u, wide ? (uint32_t)kFlagWide : (32u << kCntShift));
                 }
             } else {
                 uint32_t p = (uint32_t)t_b0 + seg_x + 32u * (uint32_t)k0;  // granule = posting index (< 2^32: checked by the host)
                 int left = seg_len - 32 * k0;
 #pragma unroll 1
-                for (int k = k0; k < k1; ++k, ++pos, p += 32u, left -= 32) sts_u2(slot(pos), p, (uint32_t)min(32, left) << 2);
+                for (int k = k0; k < k1; ++k, ++pos, p += 32u, left -= 32) sts_u2(slot(pos), p, (uint32_t)min(32, left) << kCntShift);
             }
         };
         // what follows every list: kPipe no-ops for the look-ahead of the consumer (overwritten by the next list)
-        auto finish_list = [&](int pos) {
+        // (`pos` = ring position behind the list, `len` = its length); the list's last step gets kFlagLast, which
+        // ends the consumer's drain loop without a counter
+        auto finish_list = [&](int pos, int len) {
             if (lane < kPipe) sts_u2(slot(pos + lane), 0u, 0u);
+            __syncwarp();
+            if (len > 0 && lane == 0) {
+                const uint32_t la = slot(pos - 1) + 4u;
+                uint32_t y;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(y) : "r"(la) : "memory");
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(la), "r"(y | (uint32_t)kFlagLast) : "memory");
+            }
             __syncwarp();
         };
 
@@ -335,13 +345,13 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                 if (lane < pad) sts_u2(slot(tl + len + lane), 0u, 0u);
                 len += pad;
                 if (end) {
-                    if (lane == 0) sts_u2(slot(tl + len), 0u, (uint32_t)kFlagEnd | ((uint32_t)g << 8));
+                    if (lane == 0) sts_u2(slot(tl + len), 0u, (uint32_t)kFlagEnd | ((uint32_t)g << kSubIdxShift));
                     ++len;
                 }
-                finish_list(tl + len);
+                finish_list(tl + len, len);
                 return len;
             }
-            finish_list(tl);
+            finish_list(tl, 0);
             return 0;
         };
 
@@ -447,9 +457,9 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                         write_steps(tl + my_base + pre, 0, n, n_wide);
                         const int pad = my_total - my_t - 1;
                         if (j < pad) sts_u2(slot(tl + my_base + my_t + j), 0u, 0u);
-                        if (j == TPL - 1) sts_u2(slot(tl + my_base + my_total - 1), 0u, (uint32_t)kFlagEnd | ((uint32_t)g << 8));
+                        if (j == TPL - 1) sts_u2(slot(tl + my_base + my_total - 1), 0u, (uint32_t)kFlagEnd | ((uint32_t)g << kSubIdxShift));
                     }
-                    finish_list(tl + base);
+                    finish_list(tl + base, base);
                     return base;
                 }
                 // ---- one long sub-tile (g0), a chunk of its steps per call
@@ -469,22 +479,20 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                 if (lane < pad) sts_u2(slot(tl + len + lane), 0u, 0u);
                 len += pad;
                 if (fin) {
-                    if (lane == 0) sts_u2(slot(tl + len), 0u, (uint32_t)kFlagEnd | ((uint32_t)g0 << 8));
+                    if (lane == 0) sts_u2(slot(tl + len), 0u, (uint32_t)kFlagEnd | ((uint32_t)g0 << kSubIdxShift));
                     ++len;
                 }
-                finish_list(tl + len);
+                finish_list(tl + len, len);
                 return len;
             }
-            finish_list(tl);
+            finish_list(tl, 0);
             return 0;
         };
 
         StepBuf buf[kPipe];
-        auto issue = [&](const int pos, StepBuf &b) {
-            const uint2 ds = lds_u2(slot(pos));
+        auto issue = [&](const uint2 ds, StepBuf &b) {
             b.meta = ds.y;
-            b.wide = ds.y & kFlagWide;  // the same word in every lane: a uniform branch, cheaper than a vote + guard
-            if (b.wide) {
+            if (ds.y & kFlagWide) {  // the same word in every lane: a uniform branch, cheaper than a vote + guard
                 const unsigned char *p = sbase + ((size_t)(ds.x + 2u * (uint32_t)lane) << 3);
                 b.d = ldg_stream_u4(p);
                 b.w = ldg_stream_f4(p + 512);
@@ -493,7 +501,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                 // pair would not line up with the wide step's two quads and ptxas would copy the loaded words
                 // right behind the load -- a full L2 latency stall per step (ncu, first version of this kernel)
                 uint32_t vx = dummy_off, vy = 0u;
-                if ((uint32_t)lane < ((ds.y >> 2) & 63u)) {
+                if ((uint32_t)lane < ((ds.y >> kCntShift) & 63u)) {
                     const unsigned char *p = sbase + ((size_t)(ds.x + (uint32_t)lane) << 3);
                     vx = prf::ldg_stream_u1(p);
                     vy = prf::ldg_stream_u1(p + 4);
@@ -506,7 +514,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
             // no warp barrier between steps: the warp is converged here (every branch of the loop is warp-uniform) and
             // the shared-memory pipe runs one warp's instructions in order, so a step's stores land before the next
             // step's loads; the asm statements carry "memory" clobbers, so the compiler keeps the order too
-            if (b.wide) {
+            if (b.meta & kFlagWide) {
                 const uint32_t oo[4] = {b.d.x, b.d.y, b.d.z, b.d.w};
                 const float ww[4] = {b.w.x, b.w.y, b.w.z, b.w.w};
                 float v[4];
@@ -527,7 +535,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
             }
             if (may_end && __any_sync(PR_FULL_MASK, (b.meta & kFlagEnd) != 0u)) {
                 // ---- select from the finished sub-tile (padding slots only ever hold +0.0f) and re-zero it
-                const int g_end = (int)(b.meta >> 8);
+                const int g_end = (int)(b.meta >> kSubIdxShift);
                 const int base_doc = (g_end << kSubShift) + a.doc_id_base;
                 auto consider = [&](float bs, int off) {  // warp-uniform arguments, exact score
                     const int bd = base_doc + off;
@@ -572,27 +580,32 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
 
         // ---- consumer: drain the list produced one round earlier while the next one is already in the ring, so the
         // look-ahead never runs dry.  hd = ring position of the next step to process, tl = end of what is produced.
-        int hd = 0, tl = 0, n_cur = 0;
-        bool first = true;
+        int hd = 0, tl = 0;
+        bool have_cur = false, first = true;
         while (true) {
             const int n_next = uni(fast ? produce_fast(tl) : produce(tl));
+            tl += n_next;
             if (first) {
                 first = false;
 #pragma unroll
-                for (int d = 0; d < kPipe; ++d) issue(d, buf[d]);
+                for (int d = 0; d < kPipe; ++d) issue(lds_u2(slot(d)), buf[d]);
             }
+            if (have_cur) {
+                bool last;
 #pragma unroll 1
-            for (int s0 = 0; s0 < n_cur; s0 += kPipe) {
+                do {
 #pragma unroll
-                for (int d = 0; d < kPipe; ++d) {
-                    process(buf[d], d == kPipe - 1);
-                    issue(hd + s0 + d + kPipe, buf[d]);
-                }
+                    for (int d = 0; d < kPipe; ++d) {
+                        if (d == kPipe - 1) last = (buf[d].meta & kFlagLast) != 0u;  // lists are whole rounds of kPipe steps
+                        const uint2 ds = lds_u2(slot(hd + d + kPipe));  // read early: its latency hides behind this step
+                        process(buf[d], d == kPipe - 1);
+                        issue(ds, buf[d]);
+                    }
+                    hd += kPipe;
+                } while (!last);
             }
-            hd += n_cur;
-            tl += n_next;
-            n_cur = n_next;
-            if (n_cur == 0) break;
+            have_cur = n_next > 0;
+            if (!have_cur) break;
         }
 
         float *ps = a.part_s + ((size_t)q * C + c) * K;

@@ -12,7 +12,8 @@
 //   narrow step 256 B: 32 lanes x (tile byte-offset u32, weight f32) pairs, interleaved
 //
 //   * offsets are pre-scaled byte offsets into the warp's tile (no masking / shifting per slot);
-//   * segments are padded to whole steps with (dummy word, +0.0f) slots, so there are no
+//   * segments are padded to whole steps with (dummy word, +0.0f) slots -- one dummy word per 32-slot
+//     group, in a bank the group's postings leave free -- so there are no
 //     validity masks and no alignment heads; a remainder of more than 32 postings takes one
 //     padded wide step rather than up to three narrow ones (fewer steps beat fewer slots: +10%);
 //   * inside a segment the postings are dealt round-robin over the steps' 32-slot groups in
@@ -151,14 +152,18 @@ __global__ void __launch_bounds__(256) hot_offsets_kernel(const uint32_t *tp, co
     }
 }
 
-// one warp per (hot row, sub-tile) segment: pads, then the bank-aware deal of the postings
+// one warp per (hot row, sub-tile) segment: the bank-aware deal of the postings, then the pads
+constexpr int kMaxGroups = kSub / 32 + 4;  // 32-slot groups of the longest possible segment
+
 __global__ void __launch_bounds__(256) hot_fill_kernel(const int64_t *indptr, const int32_t *doc_ids, const float *weights,
                                                        const int32_t *row_term, const uint32_t *tp, const int32_t *hot_rows,
                                                        int n_sub, int64_t n_seg, const uint32_t *hot_off, unsigned char *stream)
 {
     __shared__ int s_fill[8][32];
+    __shared__ unsigned s_banks[8][kMaxGroups];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int *fill = s_fill[w];
+    unsigned *banks = s_banks[w];  // per 32-slot group: banks its postings occupy
     const int64_t n_warps = (int64_t)gridDim.x * 8;
     for (int64_t s = (int64_t)blockIdx.x * 8 + w; s < n_seg; s += n_warps) {
         const int h = (int)(s / n_sub), g = (int)(s % n_sub);
@@ -169,18 +174,20 @@ __global__ void __launch_bounds__(256) hot_fill_kernel(const int64_t *indptr, co
         const int units = seg_units(n);
         const int n_wide = units >> 2, n_narrow = units & 3, groups = 4 * n_wide + n_narrow;
         uint32_t *out = reinterpret_cast<uint32_t *>(stream + (size_t)hot_off[(size_t)h * ((size_t)n_sub + 1) + g] * kUnitBytes);
-        // ---- padding pattern: the lane's dummy word behind the tile, weight +0.0f
-        for (int i = lane; i < n_wide * 256; i += 32) {
-            const int in_step = i & 255;
-            out[i] = in_step < 128 ? (uint32_t)(kSub + (in_step >> 2)) * 4u : 0u;
-        }
-        for (int i = lane; i < n_narrow * 64; i += 32) {
-            const int in_step = i & 63;
-            out[n_wide * 256 + i] = (in_step & 1) ? 0u : (uint32_t)(kSub + (in_step >> 1)) * 4u;
-        }
+        // word index of slot (group, lane): wide steps hold [32 x uint4 offsets][32 x float4 weights], narrow steps 32 (offset, weight) pairs
+        auto slot_words = [&](int grp, int ln, int &ow, int &ww) {
+            if (grp < 4 * n_wide) {
+                ow = (grp >> 2) * 256 + ln * 4 + (grp & 3);
+                ww = ow + 128;
+            } else {
+                ow = n_wide * 256 + (grp - 4 * n_wide) * 64 + 2 * ln;
+                ww = ow + 1;
+            }
+        };
         // ---- bank histogram -> start of every bank in bank-sorted order
         const int64_t p0 = indptr[row_term[row]] + sb;
         fill[lane] = 0;
+        for (int i = lane; i < groups; i += 32) banks[i] = 0u;
         __syncwarp();
         for (int i = lane; i < n; i += 32) atomicAdd(&fill[doc_ids[p0 + i] & 31], 1);
         __syncwarp();
@@ -193,22 +200,33 @@ __global__ void __launch_bounds__(256) hot_fill_kernel(const int64_t *indptr, co
         __syncwarp();
         fill[lane] = incl - c;
         __syncwarp();
-        // ---- deal: the i-th posting in bank order goes to group i % groups, lane i / groups
+        // ---- deal: the i-th posting in bank order goes to group i % groups, lane i / groups, so a bank's postings
+        // land in different groups (as long as it has no more than `groups` of them)
         for (int i = lane; i < n; i += 32) {
             const int d = doc_ids[p0 + i];
             const float wt = weights[p0 + i];
             const int rank = atomicAdd(&fill[d & 31], 1);
             const int grp = rank % groups, ln = rank / groups;
             int ow, ww;
-            if (grp < 4 * n_wide) {
-                ow = (grp >> 2) * 256 + ln * 4 + (grp & 3);
-                ww = ow + 128;
-            } else {
-                ow = n_wide * 256 + (grp - 4 * n_wide) * 64 + 2 * ln;
-                ww = ow + 1;
-            }
+            slot_words(grp, ln, ow, ww);
             out[ow] = (uint32_t)(d & (kSub - 1)) * 4u;
             out[ww] = __float_as_uint(wt);
+            atomicOr(&banks[grp], 1u << (d & 31));
+        }
+        __syncwarp();
+        // ---- pads: group `grp` holds ranks grp, grp + groups, ... -> its first cnt lanes; every other lane adds +0.0f
+        // to ONE dummy word behind the tile (same address in all pad lanes: a broadcast), picked in a bank none of the
+        // group's postings uses, so the padding never costs a shared-memory wavefront
+        for (int grp = 0; grp < groups; ++grp) {
+            const int cnt = (n - grp + groups - 1) / groups;
+            if (lane >= cnt) {
+                const unsigned used = banks[grp];
+                const int free_bank = __ffs(~used) - 1;  // cnt < 32 postings: a bank is free
+                int ow, ww;
+                slot_words(grp, lane, ow, ww);
+                out[ow] = (uint32_t)(kSub + free_bank) * 4u;
+                out[ww] = 0u;
+            }
         }
         __syncwarp();
     }

@@ -32,6 +32,10 @@
 #ifndef PR_LEAN_CTAS
 #define PR_LEAN_CTAS 3
 #endif
+#ifndef PR_LEAN_SIGN_EPOCH
+#define PR_LEAN_SIGN_EPOCH 1
+#endif
+#include <type_traits>
 
 namespace prl {
 
@@ -105,12 +109,12 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
     uint32_t tile_sa = (uint32_t)__cvta_generic_to_shared(tile);
     uint32_t desc_sa = (uint32_t)__cvta_generic_to_shared(desc);  // 1 KB aligned
     asm volatile("" : "+r"(tile_sa), "+r"(desc_sa));
-    const uint32_t dummy_off = (uint32_t)(kSub + lane) * 4u;
+    const uint32_t dummy_off = (uint32_t)kSub * 4u;  // all idle lanes of a narrow step share one dummy word (a broadcast)
     const unsigned char *const sbase = a.stream_base;
     const uint32_t hot_base_g = a.hot_base_g;
 
 #pragma unroll
-    for (int v = lane; v < kTileWords / 4; v += 32) tile4[v] = zero4;
+    for (int v = lane & 31; v < kTileWords / 4; v += 32) tile4[v] = zero4;
     __syncwarp();
 
     const int K = a.K, C = a.n_chunks_launch, G = a.subs_per_item;
@@ -490,6 +494,10 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
         };
 
         StepBuf buf[kPipe];
+        // ring position of the next step to process; bit 30 = sign epoch of the tile (see rmw below: set = the tile holds
+        // the previous sub-tile's sums) -- slot() masks the high bits away, and the flag costs no register of its own
+        int hd = 0;
+        constexpr int kOddBit = 1 << 30;
         auto issue = [&](const uint2 ds, StepBuf &b) {
             b.meta = ds.y;
             if (ds.y & kFlagWide) {  // the same word in every lane: a uniform branch, cheaper than a vote + guard
@@ -510,10 +518,16 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                 b.w.x = __uint_as_float(vy);
             }
         };
-        auto process = [&](const StepBuf &b, const bool may_end) {
-            // no warp barrier between steps: the warp is converged here (every branch of the loop is warp-uniform) and
-            // the shared-memory pipe runs one warp's instructions in order, so a step's stores land before the next
-            // step's loads; the asm statements carry "memory" clobbers, so the compiler keeps the order too
+        // ---- one step applied to the tile.  No warp barrier between steps: the warp is converged here (every branch
+        // of the loop is warp-uniform) and the shared-memory pipe runs one warp's instructions in order, so a step's
+        // stores land before the next step's loads; the asm statements carry "memory" clobbers, so the compiler keeps
+        // the order too.
+        // SIGN EPOCHS (halves the re-zeroing, 39% of the shared-memory wavefronts in ncu): a sub-tile that follows an
+        // unscanned one is an ODD epoch -- the tile still holds the previous sub-tile's (positive) sums, the new sums
+        // are accumulated NEGATED (v = min(word, -0) - w: a stale positive word reads as -0; negation commutes with
+        // fp32 rounding, so -v is bit-identical to the plain sum) and only the END of an odd epoch re-zeroes the tile.
+        auto rmw = [&](const StepBuf &b, auto odd_c) {
+            constexpr bool ODD = decltype(odd_c)::value;
             if (b.meta & kFlagWide) {
                 const uint32_t oo[4] = {b.d.x, b.d.y, b.d.z, b.d.w};
                 const float ww[4] = {b.w.x, b.w.y, b.w.z, b.w.w};
@@ -521,66 +535,88 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
 #pragma unroll
                 for (int x = 0; x < 4; ++x) v[x] = lds_f32(tile_sa + oo[x]);
 #pragma unroll
-                for (int x = 0; x < 4; ++x) v[x] += ww[x];
+                for (int x = 0; x < 4; ++x) v[x] = ODD ? fminf(v[x], -0.f) - ww[x] : v[x] + ww[x];
 #pragma unroll
                 for (int x = 0; x < 4; ++x) sts_f32(tile_sa + oo[x], v[x]);
-                mx = fmaxf(fmaxf(mx, v[0]), fmaxf(fmaxf(v[1], v[2]), v[3]));
-                return;
-            }
-            {
+                mx = ODD ? fminf(fminf(mx, v[0]), fminf(fminf(v[1], v[2]), v[3])) : fmaxf(fmaxf(mx, v[0]), fmaxf(fmaxf(v[1], v[2]), v[3]));
+            } else {
                 const uint32_t o = b.d.x;
-                const float v = lds_f32(tile_sa + o) + b.w.x;
+                const float x = lds_f32(tile_sa + o);
+                const float v = ODD ? fminf(x, -0.f) - b.w.x : x + b.w.x;
                 sts_f32(tile_sa + o, v);
-                mx = fmaxf(mx, v);
+                mx = ODD ? fminf(mx, v) : fmaxf(mx, v);
             }
-            if (may_end && __any_sync(PR_FULL_MASK, (b.meta & kFlagEnd) != 0u)) {
-                // ---- select from the finished sub-tile (padding slots only ever hold +0.0f) and re-zero it
-                const int g_end = (int)(b.meta >> kSubIdxShift);
-                const int base_doc = (g_end << kSubShift) + a.doc_id_base;
-                auto consider = [&](float bs, int off) {  // warp-uniform arguments, exact score
-                    const int bd = base_doc + off;
-                    if (bs >= thr && bs > theta_run && pr_beats(bs, bd, iks, ikd)) {
-                        item.insert(bs, bd, lane);
-                        item.kth(K, iks, ikd);
-                        thr = fmaxf(thr, iks);
-                    }
-                };
-                // threshold-on-update: scores only grow and weights are >= 0, so a document can enter the list only if
-                // one of its updates reached the running k-th score; that happens in well under 1% of the sub-tiles
-                // once a threshold exists, all the others are just re-zeroed
-                if (!__any_sync(PR_FULL_MASK, mx >= thr_push)) {
+        };
+        // ---- end of a sub-tile: select from it (padding words only ever hold +-0) and, if needed, re-zero it
+        auto end_subtile = [&](const uint32_t meta) {
+            const int g_end = (int)(meta >> kSubIdxShift);
+            const int base_doc = (g_end << kSubShift) + a.doc_id_base;
+            auto consider = [&](float bs, int off) {  // warp-uniform arguments, exact score
+                const int bd = base_doc + off;
+                if (bs >= thr && bs > theta_run && pr_beats(bs, bd, iks, ikd)) {
+                    item.insert(bs, bd, lane);
+                    item.kth(K, iks, ikd);
+                    thr = fmaxf(thr, iks);
+                }
+            };
+            // threshold-on-update: scores only grow and weights are >= 0, so a document can enter the list only if
+            // one of its updates reached the running k-th score; that happens in well under 1% of the sub-tiles
+            // once a threshold exists
+            const bool odd = (hd & kOddBit) != 0;
+            const float peak = odd ? -mx : mx;
+            if (!__any_sync(PR_FULL_MASK, peak >= thr_push)) {
+                if (odd || !PR_LEAN_SIGN_EPOCH) {
 #pragma unroll
-                    for (int vv = lane; vv < kSub / 4; vv += 32) tile4[vv] = zero4;
+                    for (int vv = lane & 31; vv < kSub / 4; vv += 32) tile4[vv] = zero4;
+                    hd &= ~kOddBit;
                 } else {
-                    const float thr_sel = thr;  // fixed while this sub-tile is selected from
+                    hd |= kOddBit;  // leave the sums where they are: the next sub-tile accumulates negated
+                }
+            } else {
+                const float thr_sel = thr;  // fixed while this sub-tile is selected from
+                const float sgn = odd ? -1.f : 1.f;
 #pragma unroll 4
-                    for (int vv = lane; vv < kSub / 4; vv += 32) {
-                        const float4 xb = tile4[vv];
-                        tile4[vv] = zero4;
-                        const float xs[4] = {xb.x, xb.y, xb.z, xb.w};
-                        const bool any = (xs[0] >= thr_sel) || (xs[1] >= thr_sel) || (xs[2] >= thr_sel) || (xs[3] >= thr_sel);
-                        if (__any_sync(PR_FULL_MASK, any)) {
+                for (int vv = lane & 31; vv < kSub / 4; vv += 32) {
+                    const float4 xb = tile4[vv];
+                    tile4[vv] = zero4;
+                    // odd epoch: current sums are negative, stale ones positive (-> negative here: never selected)
+                    const float xs[4] = {xb.x * sgn, xb.y * sgn, xb.z * sgn, xb.w * sgn};
+                    const bool any = (xs[0] >= thr_sel) || (xs[1] >= thr_sel) || (xs[2] >= thr_sel) || (xs[3] >= thr_sel);
+                    if (__any_sync(PR_FULL_MASK, any)) {
 #pragma unroll
-                            for (int cc = 0; cc < 4; ++cc) {
-                                unsigned mm = __ballot_sync(PR_FULL_MASK, xs[cc] >= thr_sel);
-                                while (mm) {
-                                    const int l = __ffs(mm) - 1;
-                                    mm &= mm - 1;
-                                    consider(__shfl_sync(PR_FULL_MASK, xs[cc], l), 4 * (vv - lane + l) + cc);
-                                }
+                        for (int cc = 0; cc < 4; ++cc) {
+                            unsigned mm = __ballot_sync(PR_FULL_MASK, xs[cc] >= thr_sel);
+                            while (mm) {
+                                const int l = __ffs(mm) - 1;
+                                mm &= mm - 1;
+                                consider(__shfl_sync(PR_FULL_MASK, xs[cc], l), 4 * (vv - lane + l) + cc);
                             }
                         }
                     }
                 }
-                mx = 0.f;
-                thr_push = update_mode ? thr : 0.f  /* no threshold yet: every sub-tile is scanned */;
-                __syncwarp();
+                hd &= ~kOddBit;
             }
+            mx = 0.f;
+            thr_push = update_mode ? thr : 0.f  /* no threshold yet: every sub-tile is scanned */;
+            __syncwarp();
+        };
+        // ---- one round of the ring: kPipe steps, each followed by the load of the step kPipe ahead
+        auto round = [&](auto odd_c) -> uint32_t {
+            uint32_t meta_last = 0u;
+#pragma unroll
+            for (int d = 0; d < kPipe; ++d) {
+                const uint2 ds = lds_u2(slot(hd + d + kPipe));  // read early: its latency hides behind this step
+                if (d == kPipe - 1) meta_last = buf[d].meta;
+                rmw(buf[d], odd_c);
+                issue(ds, buf[d]);
+            }
+            hd += kPipe;
+            return meta_last;
         };
 
         // ---- consumer: drain the list produced one round earlier while the next one is already in the ring, so the
         // look-ahead never runs dry.  hd = ring position of the next step to process, tl = end of what is produced.
-        int hd = 0, tl = 0;
+        int tl = 0;
         bool have_cur = false, first = true;
         while (true) {
             const int n_next = uni(fast ? produce_fast(tl) : produce(tl));
@@ -591,21 +627,21 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                 for (int d = 0; d < kPipe; ++d) issue(lds_u2(slot(d)), buf[d]);
             }
             if (have_cur) {
-                bool last;
+                uint32_t meta_last;
 #pragma unroll 1
                 do {
-#pragma unroll
-                    for (int d = 0; d < kPipe; ++d) {
-                        if (d == kPipe - 1) last = (buf[d].meta & kFlagLast) != 0u;  // lists are whole rounds of kPipe steps
-                        const uint2 ds = lds_u2(slot(hd + d + kPipe));  // read early: its latency hides behind this step
-                        process(buf[d], d == kPipe - 1);
-                        issue(ds, buf[d]);
-                    }
-                    hd += kPipe;
-                } while (!last);
+                    meta_last = (hd & kOddBit) ? round(std::true_type{}) : round(std::false_type{});
+                    // END and "last step of the list" only ever sit in the last slot of a round
+                    if (meta_last & kFlagEnd) end_subtile(meta_last);
+                } while (!(meta_last & kFlagLast));
             }
             have_cur = n_next > 0;
             if (!have_cur) break;
+        }
+        if (hd & kOddBit) {  // the item ended on an unscanned even epoch: leave a clean tile for the next item
+#pragma unroll
+            for (int vv = lane & 31; vv < kSub / 4; vv += 32) tile4[vv] = zero4;
+            __syncwarp();
         }
 
         float *ps = a.part_s + ((size_t)q * C + c) * K;

@@ -136,3 +136,27 @@ def retrieval_rounds(gate_decisions) -> int:
         if not again:
             break
     return calls
+
+
+# ---- training step, literal restatement of /root/reference/train.py --------------
+def tokens_mean_reference(cache_activation, labels, pred_lens):
+    """train.py:155-165 + 199-205: slice each sample's last pred_len tokens, concat, split, mean."""
+    result = []
+    for i in range(cache_activation.size(0)):
+        result.append(cache_activation[i, -int(pred_lens[i]):, :])
+    input_tensor = torch.cat(result, dim=0)
+    parts = torch.split(input_tensor, [int(p) for p in pred_lens.tolist()])
+    return torch.cat([torch.mean(t, dim=0, keepdim=True) for t in parts], dim=0)
+
+
+def train_step_reference(model, optim, scheduler, activations, labels, pred_lens):
+    """train.py:141-151, 210-220 (`method_2_train`) with criterion_ce on softmax(output)."""
+    x = tokens_mean_reference(activations, labels, pred_lens)
+    output = model(x)
+    logit = torch.nn.Softmax(dim=-1)(output)
+    loss = torch.nn.CrossEntropyLoss()(logit, labels)
+    loss.backward()
+    optim.step()
+    scheduler.step()
+    optim.zero_grad()
+    return round(loss.item(), 4), optim.param_groups[0]["lr"]

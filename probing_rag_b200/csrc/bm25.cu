@@ -646,7 +646,7 @@ void default_tuning(pr_bm25_tuning_t *t)
     t->cand_cap = 1024;
     t->subs_per_item = 24;
     t->warps_per_cta = 8;
-    t->docs_per_launch = 98304;
+    t->docs_per_launch = 393216;
     t->lazy_zero = 2;
     t->rescore_cost = 64;
 }

@@ -35,6 +35,12 @@
 #ifndef PR_LEAN_SIGN_EPOCH
 #define PR_LEAN_SIGN_EPOCH 1
 #endif
+#ifndef PR_LEAN_L2HINT
+// 1: wide-step loads carry an L2 evict_last policy, 2: narrow-step loads too.  Measured at 21M x 64k: L2 hit rate
+// 60% -> 94%, DRAM reads per launch 4.6 GB -> 0.5 GB, +11% queries/s (the default policy lets the streaming .nc
+// loads of one query evict the slice that the next thousand queries are about to read)
+#define PR_LEAN_L2HINT 2
+#endif
 #include <type_traits>
 
 namespace prl {
@@ -76,6 +82,26 @@ __device__ __forceinline__ uint2 ldg_stream_u2(const void *p)
     asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
     return r;
 }
+__device__ __forceinline__ uint4 ldg_hint_u4(const void *p, uint64_t pol)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ float4 ldg_hint_f4(const void *p, uint64_t pol)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ uint32_t ldg_hint_u1(const void *p, uint64_t pol)
+{
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+    return r;
+}
 __device__ __forceinline__ void sts_u2(uint32_t a, uint32_t x, uint32_t y)
 {
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
@@ -111,6 +137,10 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
     asm volatile("" : "+r"(tile_sa), "+r"(desc_sa));
     const uint32_t dummy_off = (uint32_t)kSub * 4u;  // all idle lanes of a narrow step share one dummy word (a broadcast)
     const unsigned char *const sbase = a.stream_base;
+#if PR_LEAN_L2HINT
+    uint64_t l2_keep;  // the launch's posting slice is re-read by every query of the batch: keep it in L2
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(l2_keep));
+#endif
     const uint32_t hot_base_g = a.hot_base_g;
 
 #pragma unroll
@@ -505,8 +535,13 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
             b.meta = ds.y;
             if (ds.y & kFlagWide) {  // the same word in every lane: a uniform branch, cheaper than a vote + guard
                 const unsigned char *p = sbase + ((size_t)(ds.x + 2u * (uint32_t)lane) << 3);
+#if PR_LEAN_L2HINT
+                b.d = ldg_hint_u4(p, l2_keep);
+                b.w = ldg_hint_f4(p + 512, l2_keep);
+#else
                 b.d = ldg_stream_u4(p);
                 b.w = ldg_stream_f4(p + 512);
+#endif
             } else {
                 // lanes at or past `cnt` keep (dummy word, +0.0f).  Two 32-bit loads, not one 64-bit load: a register
                 // pair would not line up with the wide step's two quads and ptxas would copy the loaded words
@@ -514,8 +549,13 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                 uint32_t vx = dummy_off, vy = 0u;
                 if ((uint32_t)lane < ((ds.y >> kCntShift) & 63u)) {
                     const unsigned char *p = sbase + ((size_t)(ds.x + (uint32_t)lane) << 3);
+#if PR_LEAN_L2HINT >= 2
+                    vx = ldg_hint_u1(p, l2_keep);
+                    vy = ldg_hint_u1(p + 4, l2_keep);
+#else
                     vx = prf::ldg_stream_u1(p);
                     vy = prf::ldg_stream_u1(p + 4);
+#endif
                 }
                 b.d.x = vx;
                 b.w.x = __uint_as_float(vy);

@@ -15,6 +15,8 @@ so a doc-range shard holds exactly the documents the single index holds for that
 """
 from __future__ import annotations
 
+import functools
+
 import numpy as np
 import torch
 
@@ -27,6 +29,7 @@ CORPUS_SEED = 1234
 QUERY_SEED = 4321
 
 
+@functools.lru_cache(maxsize=4)
 def zipf_mandelbrot_cdf(vocab: int) -> np.ndarray:
     r = np.arange(vocab, dtype=np.float64)
     p = (r + ZM_Q) ** (-ZM_S)

@@ -325,7 +325,7 @@ def test_full_size_21m_properties():
     d_qi, d_qt = torch.from_numpy(qi).to(dev), torch.from_numpy(qt).to(dev)
     gi.set_tuning(mode=2)
     s2, d2 = gi.topk(d_qi, d_qt, 10)
-    for mode in (1, 3, 4, 6, 7):
+    for mode in (1, 3, 4, 6, 7, 8):
         gi.set_tuning(mode=mode)
         s1, d1 = gi.topk(d_qi, d_qt, 10)
         assert torch.equal(s1, s2) and torch.equal(d1, d2), mode
@@ -351,7 +351,7 @@ def test_weights_outside_lazy_range_use_plain_accumulators(small_corpus):
     gi = gpu_index(idx)
     qi, qt = small_corpus["q_indptr"][:129], small_corpus["q_terms"]
     os_, od = co.retrieve_batch(idx, qi, qt, 10, n_threads=8)
-    for mode in (4, 3, 2, 7):
+    for mode in (4, 3, 2, 7, 8):
         gi.set_tuning(mode=mode, docs_per_launch=98304 if mode != 7 else 16384)
         gs, gd = run_gpu(gi, qi, qt, 10)
         assert_parity(gs, gd, os_, od)

@@ -507,6 +507,7 @@ namespace {
 
 struct Layout {
     int n_chunks, C, L;
+    std::vector<int> launch_chunk0, launch_chunks;  // launch li covers chunks [chunk0, chunk0 + chunks)
     size_t off_status, off_counters, off_theta, off_plan_theta, off_plan_mask, off_plan_m, off_run_s, off_run_d, off_part_s, off_part_d, total;
 };
 
@@ -529,7 +530,24 @@ Layout make_layout(const pr_index *ix, int32_t B, int32_t K)
     if (c < 1) c = 1;
     if (c > l.n_chunks) c = l.n_chunks > 0 ? l.n_chunks : 1;
     l.C = (int)c;
-    l.L = l.n_chunks > 0 ? (l.n_chunks + l.C - 1) / l.C : 0;
+    // Launch plan.  The first launch has no k-th score to filter with and scans every sub-tile; each later launch
+    // filters with the scores of everything before it.  So a large batch (enough work items per chunk to fill the
+    // GPU) starts with a SMALL launch and doubles -- c0, c0, 2 c0, 4 c0, ... up to C chunks -- which keeps the share
+    // of documents scored without a useful threshold small even on a short shard (8 GPUs: 2.6M documents each).
+    {
+        int64_t c0 = B > 0 ? (16384 + (int64_t)B - 1) / B : l.C;
+        if (c0 < 1) c0 = 1;
+        if (c0 > l.C || t.mode < 3) c0 = l.C;
+        int pos = 0, cl = (int)c0;
+        while (pos < l.n_chunks) {
+            const int take = cl < l.n_chunks - pos ? cl : l.n_chunks - pos;
+            l.launch_chunk0.push_back(pos);
+            l.launch_chunks.push_back(take);
+            pos += take;
+            cl = pos < l.C ? pos : l.C;
+        }
+        l.L = (int)l.launch_chunk0.size();
+    }
     size_t o = 0;
     l.off_status = o;   o = align_up(o + 64, 256);
     l.off_counters = o; o = align_up(o + (size_t)(l.L + 1) * 4, 256);
@@ -1161,7 +1179,7 @@ extern "C" int pr_bm25_topk(pr_index_t *index, int32_t n_queries, const int64_t 
                             out_scores_dev, out_doc_ids_dev, index->doc_id_base, index->n_docs);
     }
     for (int li = 0; li < l.L; ++li) {
-        const int Cl = (li + 1) * l.C <= l.n_chunks ? l.C : l.n_chunks - li * l.C;
+        const int Cl = l.launch_chunks[li], chunk0 = l.launch_chunk0[li];
         const int64_t items = (int64_t)n_queries * Cl;
         int64_t grid = (int64_t)occ * index->num_sms;
         const int64_t need = warp_mode ? (items + nw - 1) / nw : items;
@@ -1178,13 +1196,13 @@ extern "C" int pr_bm25_topk(pr_index_t *index, int32_t n_queries, const int64_t 
         PR_CUDA_CHECK(cudaMemcpyToSymbolAsync(pr_stats_launch, &li, sizeof(int), 0, cudaMemcpyHostToDevice, st));
 #endif
         if (warp_mode) {
-            w.chunk0 = li * l.C;
+            w.chunk0 = chunk0;
             w.n_chunks_launch = Cl;
             w.counter = counters + li;
             w.mode = li == 0 ? (flat_mode ? 5 : 3) : (t.mode == 8 ? 6 : t.mode);  // the first launch has no running k-th score yet
             wfn<<<(unsigned)grid, threads, smem, st>>>(w);
         } else {
-            a.chunk0 = li * l.C;
+            a.chunk0 = chunk0;
             a.n_chunks_launch = Cl;
             a.counter = counters + li;
             a.mode = li == 0 ? 1 : t.mode;

@@ -314,11 +314,12 @@ def main():
               8: "bm25_lean_kernel" if gi.aux_info().get("lean_ok") else "bm25_flat_kernel"}.get(
         tuning["mode"], "bm25_flat_kernel")
     # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/), if any
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         if tj.get("kernel") == kernel:
-            traffic = {"dram_bytes_per_launch": tj["dram_bytes_per_launch"], "source": tj.get("source")}
+            traffic = int(tj["dram_bytes_per_launch"])
+            traffic_src = tj.get("source")
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
@@ -348,6 +349,7 @@ def main():
         "gpu_launches": int(launches_per_step * args.steps),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "frac_of_8000_nominal": achieved / 8000.0, "traffic": traffic,
+                     "traffic_unit": "DRAM bytes (read + write) per launch, ncu", "traffic_source": traffic_src,
                      "peak_source": peak_src, "kernel": kernel,
                      "algorithmic_bytes_per_launch": int(alg_bytes / max(score_launches, 1)),
                      "algorithmic_bytes_per_step_rank0": int(alg_bytes),

@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libprobingrag.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
+    "-split-compile", "0",      # ptxas/NVVM of the ~70 kernel instantiations in bm25.cu on all host cores
 ]
 
 

@@ -164,24 +164,3 @@ def gate_and_retrieve(gate: ProberGate, retriever, X: torch.Tensor, q_indptr: to
     c_indptr, c_terms = select_queries(q_indptr, q_terms, out.retrieve_idx)
     scores, ids = retriever.retrieve_ids(c_indptr, c_terms, k)
     return out, scores, ids
-
-
-def smoke() -> None:
-    """One small fused forward checked against the oracle (called by __graft_entry__.smoke)."""
-    from oracle import prober_oracle as po
-    probers = []
-    for layer in po.PROBE_LAYERS:
-        p = po.OracleImprovedProbe(po.D_MODEL, po.N_CLASSES)
-        p.load_state_dict(po.make_prober_state(layer))
-        probers.append(p.eval())
-    x = po.make_hidden_states(200, seed=3)
-    ref = po.prober_logits(probers, x)
-    psum_ref, ret_ref = po.gate(ref, 0.0, 0)
-    gate = ProberGate([p.state_dict() for p in probers], device="cuda")
-    out = gate(x.cuda(), want_logits=True)
-    err = (torch.softmax(out.logits.cpu(), -1) - torch.softmax(ref, -1)).abs().max().item()
-    assert err < 1e-3, f"prober probabilities differ from the oracle by {err}"
-    margin = (psum_ref[:, 0] - psum_ref[:, 1]).abs()
-    agree = (out.retrieve.cpu() == ret_ref) | (margin < 2e-3)
-    assert bool(agree.all()), "gate decisions differ from the oracle"
-    print(f"smoke ok: fused prober (6 x 2048->512->512->2, bf16x3 tcgen05) max |dP| = {err:.2e} vs oracle")

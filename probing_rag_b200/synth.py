@@ -116,3 +116,46 @@ def corpus_block_torch(block: int, n_docs_total: int, cdf_t: torch.Tensor, seed:
     u = torch.rand(total, generator=g, device=dev, dtype=torch.float64)
     tokens = torch.searchsorted(cdf_t, u, right=True).clamp_(max=cdf_t.numel() - 1).to(torch.int32)
     return tokens, lens
+
+
+# ----------------------------------------------------------------------------- prober workload (BASELINE config 4)
+D_MODEL = 2048                          # gemma-2b d_model (Config_Maker, /root/reference/utils.py:288)
+HIDDEN = 512                            # ImprovedProbe default hidden_size (utils.py:30)
+N_CLASSES = 2                           # Config_Maker.num_classes (utils.py:290)
+PROBE_LAYERS = tuple(range(6, 17, 2))   # exp_rag.py:311
+
+
+def make_prober_state(seed: int, d_model: int = D_MODEL, hidden: int = HIDDEN,
+                      trained_like: bool = True) -> dict:
+    """Deterministic synthetic checkpoint (no trained checkpoints are shipped).
+    numpy PCG64 streams, so the same tensors regenerate on any box; LayerNorm affine
+    parameters are perturbed away from (1, 0) so they are exercised."""
+    rng = np.random.default_rng(1000 + seed)
+
+    def u(shape, bound):
+        return torch.from_numpy(rng.uniform(-bound, bound, size=shape).astype(np.float32))
+
+    sd = {
+        "layer_norm_input.weight": 1.0 + u((d_model,), 0.2 if trained_like else 0.0),
+        "layer_norm_input.bias": u((d_model,), 0.1 if trained_like else 0.0),
+        "fc1.weight": u((hidden, d_model), d_model ** -0.5),
+        "fc1.bias": u((hidden,), d_model ** -0.5),
+        "layer_norm1.weight": 1.0 + u((hidden,), 0.2 if trained_like else 0.0),
+        "layer_norm1.bias": u((hidden,), 0.1 if trained_like else 0.0),
+        "fc2.weight": u((hidden, hidden), hidden ** -0.5),
+        "fc2.bias": u((hidden,), hidden ** -0.5),
+        "layer_norm2.weight": 1.0 + u((hidden,), 0.2 if trained_like else 0.0),
+        "layer_norm2.bias": u((hidden,), 0.1 if trained_like else 0.0),
+        "fc3.weight": u((N_CLASSES, hidden), 4.0 * hidden ** -0.5),
+        "fc3.bias": u((N_CLASSES,), 0.1),
+    }
+    return sd
+
+
+def make_hidden_states(n: int, seed: int, n_probers: int = 6, d_model: int = D_MODEL) -> torch.Tensor:
+    """X[n, 6, d] = s * Normal(0,1), per-row s ~ LogUniform(10, 300): a sum of up to 149
+    residual-stream vectors (exp_rag.py:386)."""
+    rng = np.random.default_rng(7000 + seed)
+    x = rng.standard_normal((n, n_probers, d_model), dtype=np.float32)
+    s = np.exp(rng.uniform(np.log(10.0), np.log(300.0), size=(n, 1, 1))).astype(np.float32)
+    return torch.from_numpy(x * s)

@@ -13,7 +13,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import prober_oracle as po  # noqa: E402
+from probing_rag_b200 import synth as po  # noqa: E402  (synthetic probers + hidden states)
 from probing_rag_b200.prober import ImprovedProbe, ProberGate  # noqa: E402
 
 

@@ -355,3 +355,33 @@ def test_weights_outside_lazy_range_use_plain_accumulators(small_corpus):
         gi.set_tuning(mode=mode, docs_per_launch=98304 if mode != 7 else 16384)
         gs, gd = run_gpu(gi, qi, qt, 10)
         assert_parity(gs, gd, os_, od)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_shapes(seed):
+    """Ragged shapes the Zipf workload never produces: 1..9000 documents (one sub-tile, a partial last sub-tile,
+    exactly 2048 / 4096), tiny vocabularies (every term is heavy: thousands of postings per sub-tile, many
+    wide steps, lists longer than one descriptor list), empty and 1..48-term queries with duplicates."""
+    rng = np.random.default_rng(900 + seed)
+    n_docs = int([1, 31, 2047, 2048, 2049, 4096, 5000, 9000, 700, 4097, 6143, 8192][seed])
+    vocab = int(rng.choice([4, 16, 200, 3000]))
+    lens = rng.integers(1, 40, size=n_docs).astype(np.int32)
+    toks = rng.integers(0, vocab, size=int(lens.sum())).astype(np.int32)
+    idx = bo.build_index(toks, lens, vocab)
+    nq = 97
+    qlens = rng.integers(0, 49, size=nq)
+    qlens[:3] = [0, 1, 48]
+    qi = np.concatenate([[0], np.cumsum(qlens)]).astype(np.int64)
+    qt = rng.integers(0, vocab, size=int(qlens.sum())).astype(np.int32)
+    keep = idx["df"][qt] > 0                     # bm25s drops unknown terms on the query side
+    qid = np.repeat(np.arange(nq), qlens)[keep]
+    qt = qt[keep]
+    qi = np.concatenate([[0], np.cumsum(np.bincount(qid, minlength=nq))]).astype(np.int64)
+    gi = gpu_index(idx)
+    for k in (1, min(10, n_docs), min(100, n_docs)):
+        os_, od = co.retrieve_batch(idx, qi, qt, k, n_threads=8)
+        for tun in (dict(mode=8), dict(mode=8, subs_per_item=1, warps_per_cta=4, docs_per_launch=2048, min_items=1),
+                    dict(mode=8, subs_per_item=2, warps_per_cta=12, docs_per_launch=4096, min_items=1), dict(mode=6)):
+            gi.set_tuning(**tun)
+            gs, gd = run_gpu(gi, qi, qt, k)
+            assert_parity(gs, gd, os_, od)

@@ -30,6 +30,7 @@
 #include "bm25_warp.cuh"
 #include "bm25_flat.cuh"
 #include "bm25_lean.cuh"
+#include "bm25_kernels.h"
 
 namespace {
 
@@ -580,68 +581,12 @@ score_fn_t pick_score_fn(int threads, int E)
     return pick_score<512, 2>(E);
 }
 
-typedef void (*warp_fn_t)(const prw::WarpArgs);
-
-template <int NW, bool LAZY>
-warp_fn_t pick_warp(int E)
-{
-    if (E == 1) return prw::bm25_warp_kernel<NW, 1, LAZY>;
-    if (E == 2) return prw::bm25_warp_kernel<NW, 2, LAZY>;
-    return prw::bm25_warp_kernel<NW, 4, LAZY>;
-}
-
-warp_fn_t pick_warp_fn(int nw, int E, bool lazy)
-{
-    if (lazy) {
-        if (nw == 4) return pick_warp<4, true>(E);
-        if (nw == 9) return pick_warp<9, true>(E);
-        if (nw == 13) return pick_warp<13, true>(E);
-        if (nw == 16) return pick_warp<16, true>(E);
-        return pick_warp<8, true>(E);
-    }
-    if (nw == 4) return pick_warp<4, false>(E);
-    if (nw == 9) return pick_warp<9, false>(E);
-    if (nw == 13) return pick_warp<13, false>(E);
-    if (nw == 16) return pick_warp<16, false>(E);
-    return pick_warp<8, false>(E);
-}
-
-template <int NW, bool SKIP>
-warp_fn_t pick_flat(int E)
-{
-    if (E == 1) return prf::bm25_flat_kernel<NW, 1, SKIP>;
-    if (E == 2) return prf::bm25_flat_kernel<NW, 2, SKIP>;
-    return prf::bm25_flat_kernel<NW, 4, SKIP>;
-}
-
-warp_fn_t pick_flat_fn(int nw, int E, bool skip)
-{
-    if (skip) {
-        if (nw == 4) return pick_flat<4, true>(E);
-        if (nw == 12) return pick_flat<12, true>(E);
-        return pick_flat<8, true>(E);
-    }
-    if (nw == 4) return pick_flat<4, false>(E);
-    if (nw == 10) return pick_flat<10, false>(E);   // 2 CTAs of 10 warps: 20 warps per SM, 96 registers per thread
-    if (nw == 12) return pick_flat<12, false>(E);
-    return pick_flat<8, false>(E);
-}
-
-template <int NW>
-warp_fn_t pick_lean(int E)
-{
-    if (E == 1) return prl::bm25_lean_kernel<NW, 1>;
-    if (E == 2) return prl::bm25_lean_kernel<NW, 2>;
-    return prl::bm25_lean_kernel<NW, 4>;
-}
-
-warp_fn_t pick_lean_fn(int nw, int E)
-{
-    if (nw == 4) return pick_lean<4>(E);
-    if (nw == 10) return pick_lean<10>(E);
-    if (nw == 12) return pick_lean<12>(E);
-    return pick_lean<8>(E);
-}
+// The templated warp-autonomous kernels are instantiated in their own translation units (bm25_kernels_*.cu) so the
+// library compiles in parallel; bm25_kernels.h declares the pickers.
+using prk::pick_flat_fn;
+using prk::pick_lean_fn;
+using prk::pick_warp_fn;
+using prk::warp_fn_t;
 
 int launch_merge(int E, dim3 grid, cudaStream_t st, const float *ps, const int32_t *pd, int C,
                  int64_t sq, int64_t sc, float *rs, int32_t *rd, float *rt, int B, int K, int fin,

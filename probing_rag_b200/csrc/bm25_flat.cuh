@@ -119,7 +119,7 @@ __device__ __forceinline__ float ldg_stream_f1(const void *p)
 // query-token order in fp32 (absent terms add +0.0f, which is exact), i.e. exactly what the
 // exhaustive modes accumulate.  `offs` = the candidates' tile offsets in shared memory, n of them
 // (n * nq <= 32).  Returns the score of candidate l / nq.  Warp-collective; rare, kept out of line.
-__device__ __noinline__ float flat_rescore(const int32_t *__restrict__ q_terms, int nq, const int64_t *__restrict__ indptr,
+static __device__ __noinline__ float flat_rescore(const int32_t *__restrict__ q_terms, int nq, const int64_t *__restrict__ indptr,
                                            const int32_t *__restrict__ heavy_row, const uint32_t *__restrict__ tp,
                                            const int32_t *__restrict__ doc_ids, const float *__restrict__ weights,
                                            int n_terms, int n_sub, int g, const int32_t *offs, int n)
@@ -163,7 +163,7 @@ __device__ __noinline__ float flat_rescore(const int32_t *__restrict__ q_terms, 
 // a remaining list that alone reaches the push threshold theta - M costs `rescore_cost` more
 // (fraction estimated from the list's max / 1% / 10% weight levels).  The choice only affects
 // speed: any safe prefix gives bit-identical results.
-__global__ void __launch_bounds__(128) bm25_plan_kernel(const int64_t *__restrict__ q_indptr, const int32_t *__restrict__ q_terms,
+static __global__ void __launch_bounds__(128) bm25_plan_kernel(const int64_t *__restrict__ q_indptr, const int32_t *__restrict__ q_terms,
                                                        const int64_t *__restrict__ indptr, const int32_t *__restrict__ heavy_row,
                                                        const float *__restrict__ term_maxw, const float *__restrict__ row_q,
                                                        const float *__restrict__ run_theta, float *plan_theta,

@@ -55,7 +55,7 @@ __host__ __device__ __forceinline__ int seg_units(int n)
 }
 
 // hot_of_row[r] = exclusive rank of row r among the rows with df >= min_df, or -1; one warp.
-__global__ void hot_assign_kernel(const int64_t *indptr, const int32_t *row_term, int n_rows, int64_t min_df,
+static __global__ void hot_assign_kernel(const int64_t *indptr, const int32_t *row_term, int n_rows, int64_t min_df,
                                   int32_t *hot_of_row, int32_t *hot_rows, int32_t *n_hot)
 {
     const int lane = threadIdx.x & 31;
@@ -88,7 +88,7 @@ __device__ __forceinline__ int hot_seg_len(const uint32_t *tp, const int32_t *ho
 constexpr int kScanChunk = 2048;  // segments per block of the offset scan (256 threads x 8)
 
 // block sums of seg_units over chunks of the flat (hot row, sub-tile) segment array
-__global__ void __launch_bounds__(256) hot_units_kernel(const uint32_t *tp, const int32_t *hot_rows, int n_sub, int64_t n_seg,
+static __global__ void __launch_bounds__(256) hot_units_kernel(const uint32_t *tp, const int32_t *hot_rows, int n_sub, int64_t n_seg,
                                                         uint32_t *block_sum)
 {
     __shared__ uint32_t ws[8];
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) hot_units_kernel(const uint32_t *tp, cons
     }
 }
 
-__global__ void hot_block_scan_kernel(uint32_t *block_sum, int n_blocks, uint32_t *total)  // one thread: a few thousand blocks
+static __global__ void hot_block_scan_kernel(uint32_t *block_sum, int n_blocks, uint32_t *total)  // one thread: a few thousand blocks
 {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         uint32_t acc = 0;
@@ -120,7 +120,7 @@ __global__ void hot_block_scan_kernel(uint32_t *block_sum, int n_blocks, uint32_
 }
 
 // hot_off[h][g] = units before segment (h, g); hot_off[h][n_sub] = units before row h+1
-__global__ void __launch_bounds__(256) hot_offsets_kernel(const uint32_t *tp, const int32_t *hot_rows, int n_sub, int64_t n_seg,
+static __global__ void __launch_bounds__(256) hot_offsets_kernel(const uint32_t *tp, const int32_t *hot_rows, int n_sub, int64_t n_seg,
                                                           const uint32_t *block_off, uint32_t *hot_off)
 {
     __shared__ uint32_t ws[8];
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) hot_offsets_kernel(const uint32_t *tp, co
 // one warp per (hot row, sub-tile) segment: the bank-aware deal of the postings, then the pads
 constexpr int kMaxGroups = kSub / 32 + 4;  // 32-slot groups of the longest possible segment
 
-__global__ void __launch_bounds__(256) hot_fill_kernel(const int64_t *indptr, const int32_t *doc_ids, const float *weights,
+static __global__ void __launch_bounds__(256) hot_fill_kernel(const int64_t *indptr, const int32_t *doc_ids, const float *weights,
                                                        const int32_t *row_term, const uint32_t *tp, const int32_t *hot_rows,
                                                        int n_sub, int64_t n_seg, const uint32_t *hot_off, unsigned char *stream)
 {

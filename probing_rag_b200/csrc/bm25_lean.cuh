@@ -111,7 +111,7 @@ __device__ __forceinline__ void sts_u2(uint32_t a, uint32_t x, uint32_t y)
 __device__ __forceinline__ int uni(int v) { return __reduce_max_sync(PR_FULL_MASK, v); }
 
 // cold stream: posting p of the CSR as (tile byte offset, weight bits)
-__global__ void __launch_bounds__(256) cold_fill_kernel(const int32_t *__restrict__ doc_ids, const float *__restrict__ weights,
+static __global__ void __launch_bounds__(256) cold_fill_kernel(const int32_t *__restrict__ doc_ids, const float *__restrict__ weights,
                                                         int64_t nnz, uint2 *__restrict__ cold)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -616,7 +616,10 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                     hd |= kOddBit;  // leave the sums where they are: the next sub-tile accumulates negated
                 }
             } else {
-                const float thr_sel = thr;  // fixed while this sub-tile is selected from
+                // `thr` is read live: it rises with every insert (the k-th score of the item's list), and a document below
+                // it can no longer enter the list -- in a launch without thresholds this cuts the candidates visited in an
+                // item's first sub-tile from every positive score (~450) to a few dozen.  The visiting order does not
+                // matter: the list is the top-k under a total order (score desc, doc id asc).
                 const float sgn = odd ? -1.f : 1.f;
 #pragma unroll 4
                 for (int vv = lane & 31; vv < kSub / 4; vv += 32) {
@@ -624,15 +627,15 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                     tile4[vv] = zero4;
                     // odd epoch: current sums are negative, stale ones positive (-> negative here: never selected)
                     const float xs[4] = {xb.x * sgn, xb.y * sgn, xb.z * sgn, xb.w * sgn};
-                    const bool any = (xs[0] >= thr_sel) || (xs[1] >= thr_sel) || (xs[2] >= thr_sel) || (xs[3] >= thr_sel);
-                    if (__any_sync(PR_FULL_MASK, any)) {
+                    const float m4 = fmaxf(fmaxf(xs[0], xs[1]), fmaxf(xs[2], xs[3]));
+                    if (__any_sync(PR_FULL_MASK, m4 >= thr)) {
 #pragma unroll
                         for (int cc = 0; cc < 4; ++cc) {
-                            unsigned mm = __ballot_sync(PR_FULL_MASK, xs[cc] >= thr_sel);
+                            unsigned mm = __ballot_sync(PR_FULL_MASK, xs[cc] >= thr);
                             while (mm) {
                                 const int l = __ffs(mm) - 1;
                                 mm &= mm - 1;
-                                consider(__shfl_sync(PR_FULL_MASK, xs[cc], l), 4 * (vv - lane + l) + cc);
+                                consider(__shfl_sync(PR_FULL_MASK, xs[cc], l), 4 * (vv - (lane & 31) + l) + cc);
                             }
                         }
                     }

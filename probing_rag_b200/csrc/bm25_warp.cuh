@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 6 : NW <= 9 ? 3 : NW <= 13
 }
 
 // ---------------------------------------------------------------- index-side tables (aux)
-__global__ void count_heavy_kernel(const int64_t *indptr, int n_terms, int64_t min_df, int32_t *count)
+static __global__ void count_heavy_kernel(const int64_t *indptr, int n_terms, int64_t min_df, int32_t *count)
 {
     int local = 0;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_terms; t += (int64_t)gridDim.x * blockDim.x)
@@ -484,7 +484,7 @@ __global__ void count_heavy_kernel(const int64_t *indptr, int n_terms, int64_t m
 }
 
 // heavy_row[t] = exclusive count of heavy terms before t (block-local scan + block offsets)
-__global__ void heavy_block_count_kernel(const int64_t *indptr, int n_terms, int64_t min_df, int32_t *block_cnt)
+static __global__ void heavy_block_count_kernel(const int64_t *indptr, int n_terms, int64_t min_df, int32_t *block_cnt)
 {
     __shared__ int s;
     if (threadIdx.x == 0) s = 0;
@@ -497,7 +497,7 @@ __global__ void heavy_block_count_kernel(const int64_t *indptr, int n_terms, int
     if (threadIdx.x == 0) block_cnt[blockIdx.x] = s;
 }
 
-__global__ void heavy_block_scan_kernel(int32_t *block_cnt, int n_blocks)  // one thread: n_blocks is a few thousand
+static __global__ void heavy_block_scan_kernel(int32_t *block_cnt, int n_blocks)  // one thread: n_blocks is a few thousand
 {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         int acc = 0;
@@ -509,7 +509,7 @@ __global__ void heavy_block_scan_kernel(int32_t *block_cnt, int n_blocks)  // on
     }
 }
 
-__global__ void heavy_assign_kernel(const int64_t *indptr, int n_terms, int64_t min_df, const int32_t *block_off,
+static __global__ void heavy_assign_kernel(const int64_t *indptr, int n_terms, int64_t min_df, const int32_t *block_off,
                                     int32_t *heavy_row, int32_t *row_term)
 {
     __shared__ int warp_cnt[32];
@@ -528,7 +528,7 @@ __global__ void heavy_assign_kernel(const int64_t *indptr, int n_terms, int64_t 
     }
 }
 
-__global__ void tp_fill_kernel(const int64_t *indptr, const int32_t *doc_ids, const int32_t *row_term, int n_rows,
+static __global__ void tp_fill_kernel(const int64_t *indptr, const int32_t *doc_ids, const int32_t *row_term, int n_rows,
                                int n_sub, uint32_t *tp)
 {
     const int64_t total = (int64_t)n_rows * (n_sub + 1);
@@ -550,7 +550,7 @@ __global__ void tp_fill_kernel(const int64_t *indptr, const int32_t *doc_ids, co
 // row_q[2r], row_q[2r+1] = weights of tabulated row r that at most ~1% / ~10% of its postings reach
 // (lower edges of a 256-bin histogram over [0, term_maxw]).  Only the cost model of the mode-7
 // planner reads them, so they need not be exact.  One CTA per row.
-__global__ void __launch_bounds__(256) row_quantile_kernel(const int64_t *indptr, const float *weights, const int32_t *row_term,
+static __global__ void __launch_bounds__(256) row_quantile_kernel(const int64_t *indptr, const float *weights, const int32_t *row_term,
                                                           const float *term_maxw, int n_rows, float *row_q)
 {
     __shared__ int hist[256];
@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(256) row_quantile_kernel(const int64_t *indptr
 
 // term_maxw[t] = largest weight in the list of term t (0 for an empty list); one warp per term.
 // Upper bound of any one posting's contribution, used by the rank-safe term skipping of mode 7.
-__global__ void __launch_bounds__(256) term_maxw_kernel(const int64_t *indptr, const float *weights, int n_terms, float *term_maxw)
+static __global__ void __launch_bounds__(256) term_maxw_kernel(const int64_t *indptr, const float *weights, int n_terms, float *term_maxw)
 {
     const int lane = threadIdx.x & 31;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;

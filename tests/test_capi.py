@@ -34,3 +34,21 @@ def test_version_and_argument_errors_without_gpu():
     assert L.pr_bm25_workspace_bytes(None, 4, 10) == 0
     h = ctypes.c_void_p()
     assert L.pr_index_create(ctypes.byref(h), 0, 10, 0, 10, 4, 0, None, None, None) == _lib.PR_EINVAL
+
+
+def test_default_scoring_kernel_resource_budget():
+    """Guard against a silently worse build of the default BM25 kernel: 3 CTAs x 8 warps per SM need <= 80
+    registers per thread, and a stack frame beyond a few words means ptxas spilled inside the step loop
+    (seen once with nvcc -split-compile: same source, 104 bytes of stack, -21% queries/s)."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        import pytest
+        pytest.skip("cuobjdump not on PATH")
+    out = subprocess.run(["cuobjdump", "-res-usage", build.build()], capture_output=True, text=True).stdout
+    lines = out.splitlines()
+    hits = [lines[i + 1] for i, l in enumerate(lines) if "bm25_lean_kernelILi8ELi1E" in l and i + 1 < len(lines)]
+    assert hits, "default kernel bm25_lean_kernel<8, 1> not found in the library"
+    m = re.search(r"REG:(\d+) STACK:(\d+)", hits[0])
+    assert m, hits[0]
+    assert int(m.group(1)) <= 80 and int(m.group(2)) <= 48, hits[0]

@@ -106,3 +106,26 @@ def test_doc_range_shards_merge_to_single_index():
             ss.append(s); dd.append(d)
         ms, md = bo.merge_topk(np.stack(ss), np.stack(dd), 10)
         assert np.array_equal(ms, ref_s) and np.array_equal(md, ref_d), g
+
+
+def test_bm25s_readme_quickstart_scores():
+    """Sanity anchor on the variant constants (NOT a pin: recalled from the published bm25s README quickstart, which
+    cannot be fetched offline).  Corpus of four sentences, query "does the fish purr like a cat?", tokenised with
+    bm25s' English stop-word list and no stemming; the README prints the two hits as `score: 1.06` and `score: 0.48`.
+    Lucene idf with k1 = 1.5, b = 0.75 reproduces both to the printed digits; Robertson idf would give 0.75 / 0.34,
+    BM25+ / BM25L other values again."""
+    from probing_rag_b200 import text
+    corpus = ["a cat is a feline and likes to purr", "a dog is the human's best friend and loves to play",
+              "a bird is a beautiful animal that can fly", "a fish is a creature that lives in water and swims"]
+    docs = [text.split_tokens(d) for d in corpus]
+    assert [len(d) for d in docs] == [4, 6, 5, 5]                 # after the 33-word stop list
+    vocab = {}
+    for d in docs:
+        for w in d:
+            vocab.setdefault(w, len(vocab))
+    idx = bo.build_index_loop([np.array([vocab[w] for w in d]) for d in docs], len(vocab))
+    q = np.array([vocab[w] for w in text.split_tokens("does the fish purr like a cat?") if w in vocab], dtype=np.int32)
+    s = bo.score_query(idx, q)
+    assert f"{s[0]:.2f}" == "1.06" and f"{s[3]:.2f}" == "0.48" and s[1] == 0 and s[2] == 0
+    sc, ids = bo.topk_canonical(s, 2)
+    assert ids.tolist() == [0, 3]

@@ -508,6 +508,7 @@ namespace {
 
 struct Layout {
     int n_chunks, C, L;
+    int G;  // sub-tiles per work item actually used (warp modes): tuning.subs_per_item, halved for small batches
     std::vector<int> launch_chunk0, launch_chunks;  // launch li covers chunks [chunk0, chunk0 + chunks)
     size_t off_status, off_counters, off_theta, off_plan_theta, off_plan_mask, off_plan_m, off_run_s, off_run_d, off_part_s, off_part_d, total;
 };
@@ -519,9 +520,13 @@ Layout make_layout(const pr_index *ix, int32_t B, int32_t K)
     const pr_bm25_tuning_t &t = ix->tuning;
     Layout l;
     int64_t c = B > 0 ? ((int64_t)t.min_items + B - 1) / B : 1;
+    l.G = t.subs_per_item;
     if (t.mode >= 3) {
-        l.n_chunks = (ix->n_sub + t.subs_per_item - 1) / t.subs_per_item;
-        const int64_t chunk_docs = (int64_t)t.subs_per_item * prw::kSub;
+        // a small batch (the reference calls retrieve() with ONE query) has too few (query, chunk) items to fill
+        // 148 SMs x 24 warps: cut the items shorter until there are a few thousand of them
+        while (l.G > 1 && (int64_t)B * ((ix->n_sub + l.G - 1) / l.G) < 8192) l.G = (l.G + 1) / 2;
+        l.n_chunks = (ix->n_sub + l.G - 1) / l.G;
+        const int64_t chunk_docs = (int64_t)l.G * prw::kSub;
         const int64_t c2 = (t.docs_per_launch + chunk_docs - 1) / chunk_docs;
         if (c2 > c) c = c2;
     } else {
@@ -1117,7 +1122,7 @@ extern "C" int pr_bm25_topk(pr_index_t *index, int32_t n_queries, const int64_t 
     w.n_queries = n_queries;
     w.K = k;
     w.n_sub = index->n_sub;
-    w.subs_per_item = t.subs_per_item;
+    w.subs_per_item = l.G;
 
     if (l.L == 0) {  // shard without documents: only the (empty) finalisation
         return launch_merge(E, mgrid, st, part_s, part_d, 0, 0, 0, run_s, run_d, theta, n_queries, k, 1,

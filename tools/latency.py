@@ -1,0 +1,45 @@
+"""Small-batch latency of pr_bm25_topk on the full-size index (the reference calls retrieve() one query at a time).
+
+    python tools/latency.py [--n-docs N] [--batches 1,8,64,512,4096] [--k 10]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from probing_rag_b200 import synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n-docs", type=int, default=synth.N_DOCS_WIKI)
+    ap.add_argument("--vocab", type=int, default=1 << 22)
+    ap.add_argument("--batches", default="1,8,64,512,4096")
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--reps", type=int, default=20)
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    gi, qi, qt = bench.build_workload(args.n_docs, args.vocab, 4096, dev)
+    for b in [int(x) for x in args.batches.split(",")]:
+        d_qi = torch.from_numpy(qi[:b + 1]).to(dev)
+        d_qt = torch.from_numpy(qt[:qi[b]]).to(dev)
+        for _ in range(3):
+            gi.topk(d_qi, d_qt, args.k)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.reps):
+            gi.topk(d_qi, d_qt, args.k, check_status=False)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.reps
+        print(json.dumps({"batch": b, "k": args.k, "ms_per_call": ms, "qps": b / ms * 1e3, "launches": gi.last_launches}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,25 +1,26 @@
-// Lean-step BM25 scoring kernel (tuning.mode 8): the flat-step design of bm25_flat.cuh -- one warp
-// owns a (query, document-range) work item and a private 2048-document fp32 score tile in shared
-// memory, applies the query's terms in query-token order (one rounded fp32 add per posting:
-// bit-identical to the reference's dense accumulator) and runs ONE loop over step descriptors with
-// the loads issued kPipe steps ahead -- with the per-step instruction overhead cut roughly in half.
-// ncu on the flat kernel (profiles/r01/v4_flat_kernel_ncu_summary.txt) showed ~60 warp
-// instructions per 128-slot step and ~50 per 32-slot step, most of them control: three step kinds
-// decoded by divergent-looking branches (BSSY/BSYNC pairs, BRA.DIV guards in front of every vote),
-// two descriptor lists with bounds checks, 64-bit address assembly for CSR steps, S2R
-// rematerialisation.  Here:
+// Lean-step BM25 scoring kernel (tuning.mode 8, the default): the flat-step design of bm25_flat.cuh -- one warp
+// owns a (query, document-range) work item and a private 2048-document fp32 score tile in shared memory, applies
+// the query's terms in query-token order (one rounded fp32 add per posting: bit-identical to the reference's dense
+// accumulator) and runs ONE loop over step descriptors with the loads issued kPipe steps ahead -- with the
+// per-step overhead cut by a third and the shared-memory traffic by a third.  ncu on the flat kernel
+// (profiles/r01/v4_flat_kernel_ncu_summary.txt) showed ~60 warp instructions per 128-slot step and ~50 per 32-slot
+// step, most of them control: three step kinds decoded by nested branches, BRA.DIV guards in front of every vote,
+// two descriptor lists with bounds checks, 64-bit address assembly for CSR steps, S2R rematerialisation, a per-step
+// candidate list.  Here (history and numbers in DESIGN.md 4.1):
 //
-//   * ONE posting address space.  Next to the hot stream the index keeps a COLD stream: every CSR
-//     posting as an interleaved (pre-scaled tile byte offset, weight) pair, 8 bytes, at granule
-//     index = posting index.  Hot narrow units are interleaved pairs too.  A descriptor is
-//     (granule index u32, flags): address = base + 8 * (granule + lane [* 2]).  Two step shapes
-//     remain: WIDE (4 slots per lane, two 128-bit loads) and NARROW (one 64-bit load for the lanes
-//     below `cnt`; the others add +0.0f to their dummy word).  No-op and END steps are narrow steps
-//     with cnt = 0, so there is no third kind.
-//   * Every branch of the step loop is taken on a VOTED predicate or a REDUX-ed counter, which
-//     ptxas knows to be warp-uniform: no reconvergence barriers, no divergence guards.
-//   * The two descriptor lists become one 128-entry ring; each produced list is followed by kPipe
-//     no-op descriptors, so the look-ahead never needs a bounds check.
+//   * ONE posting address space.  Next to the hot stream the index keeps a COLD stream: every CSR posting as an
+//     interleaved (pre-scaled tile byte offset, weight) pair, 8 bytes, at granule index = posting index; hot narrow
+//     units are interleaved pairs too.  A descriptor is (granule index u32, flags): address = base + 8 * (granule +
+//     lane [* 2]).  Two step shapes remain: WIDE (4 slots per lane, two 128-bit loads) and NARROW (two 32-bit loads
+//     for the lanes below `cnt`; the others add +0.0f to a dummy word).  No-op and END steps are narrow steps with
+//     cnt = 0, so there is no third kind, and every per-step branch tests one flag bit of a word all lanes hold.
+//   * The two descriptor lists become one 128-entry ring; each produced list ends with a flagged descriptor (no
+//     loop counter) and is followed by kPipe no-op descriptors, so the look-ahead never needs a bounds check.
+//   * Threshold-on-update without candidate lists: each lane tracks the largest accumulator value it wrote; one
+//     vote at the end of a sub-tile decides whether the tile has to be scanned at all.
+//   * Sign epochs: every other sub-tile accumulates negated sums on top of the previous sub-tile's, so the tile is
+//     re-zeroed half as often.
+//   * Posting loads carry an L2 evict_last policy; items are handed out chunk-major.
 //
 // Mode 7 (rank-safe term skipping) stays with the flat kernel.
 #pragma once
@@ -106,8 +107,7 @@ __device__ __forceinline__ void sts_u2(uint32_t a, uint32_t x, uint32_t y)
 {
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
 }
-// warp-uniform copy of a value all lanes agree on; REDUX writes a uniform register, so ptxas
-// treats everything derived from it (loop bounds, branch conditions) as convergent
+// warp-uniform copy of a value all lanes agree on (REDUX writes a uniform register)
 __device__ __forceinline__ int uni(int v) { return __reduce_max_sync(PR_FULL_MASK, v); }
 
 // cold stream: posting p of the CSR as (tile byte offset, weight bits)

@@ -543,22 +543,22 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                 b.w = ldg_stream_f4(p + 512);
 #endif
             } else {
-                // lanes at or past `cnt` keep (dummy word, +0.0f).  Two 32-bit loads, not one 64-bit load: a register
-                // pair would not line up with the wide step's two quads and ptxas would copy the loaded words
-                // right behind the load -- a full L2 latency stall per step (ncu, first version of this kernel)
-                uint32_t vx = dummy_off, vy = 0u;
+                // lanes at or past `cnt` keep (dummy word, +0.0f).  ONE 64-bit load into (d.x, d.y) -- the first half of
+                // the offset quad, an aligned register pair -- so a narrow step's weight travels in d.y.  (Loading the
+                // pair into (d.x, w.x) made ptxas copy the words right behind the load: a full L2 latency stall per
+                // step; two 32-bit loads avoid that too but cost two extra L1TEX wavefronts per step.)
+                uint2 v = make_uint2(dummy_off, 0u);
                 if ((uint32_t)lane < ((ds.y >> kCntShift) & 63u)) {
                     const unsigned char *p = sbase + ((size_t)(ds.x + (uint32_t)lane) << 3);
 #if PR_LEAN_L2HINT >= 2
-                    vx = ldg_hint_u1(p, l2_keep);
-                    vy = ldg_hint_u1(p + 4, l2_keep);
+                    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;"
+                                 : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(l2_keep));
 #else
-                    vx = prf::ldg_stream_u1(p);
-                    vy = prf::ldg_stream_u1(p + 4);
+                    v = ldg_stream_u2(p);
 #endif
                 }
-                b.d.x = vx;
-                b.w.x = __uint_as_float(vy);
+                b.d.x = v.x;
+                b.d.y = v.y;
             }
         };
         // ---- one step applied to the tile.  No warp barrier between steps: the warp is converged here (every branch
@@ -585,7 +585,8 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
             } else {
                 const uint32_t o = b.d.x;
                 const float x = lds_f32(tile_sa + o);
-                const float v = ODD ? fminf(x, -0.f) - b.w.x : x + b.w.x;
+                const float w = __uint_as_float(b.d.y);  // narrow step: (offset, weight) = (d.x, d.y)
+                const float v = ODD ? fminf(x, -0.f) - w : x + w;
                 sts_f32(tile_sa + o, v);
                 mx = ODD ? fminf(mx, v) : fmaxf(mx, v);
             }

@@ -137,6 +137,9 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
     asm volatile("" : "+r"(tile_sa), "+r"(desc_sa));
     const uint32_t dummy_off = (uint32_t)kSub * 4u;  // all idle lanes of a narrow step share one dummy word (a broadcast)
     const unsigned char *const sbase = a.stream_base;
+    // per-lane bases of the two step shapes, so a step's address is one IMAD.WIDE (granule * 8 + base)
+    const unsigned char *wide_base = sbase + lane * 16, *narrow_base = sbase + lane * 8;
+    asm volatile("" : "+l"(wide_base), "+l"(narrow_base));
 #if PR_LEAN_L2HINT
     uint64_t l2_keep;  // the launch's posting slice is re-read by every query of the batch: keep it in L2
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(l2_keep));
@@ -534,7 +537,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
         auto issue = [&](const uint2 ds, StepBuf &b) {
             b.meta = ds.y;
             if (ds.y & kFlagWide) {  // the same word in every lane: a uniform branch, cheaper than a vote + guard
-                const unsigned char *p = sbase + ((size_t)(ds.x + 2u * (uint32_t)lane) << 3);
+                const unsigned char *p = wide_base + ((size_t)ds.x << 3);
 #if PR_LEAN_L2HINT
                 b.d = ldg_hint_u4(p, l2_keep);
                 b.w = ldg_hint_f4(p + 512, l2_keep);
@@ -549,7 +552,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                 // step; two 32-bit loads avoid that too but cost two extra L1TEX wavefronts per step.)
                 uint2 v = make_uint2(dummy_off, 0u);
                 if ((uint32_t)lane < ((ds.y >> kCntShift) & 63u)) {
-                    const unsigned char *p = sbase + ((size_t)(ds.x + (uint32_t)lane) << 3);
+                    const unsigned char *p = narrow_base + ((size_t)ds.x << 3);
 #if PR_LEAN_L2HINT >= 2
                     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;"
                                  : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(l2_keep));

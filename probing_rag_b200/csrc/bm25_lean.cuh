@@ -63,10 +63,10 @@ constexpr int kPipe = PR_LEAN_PIPE;
 static_assert(2 * kListCap + kPipe <= kRing, "ring too small");
 static_assert(kListCap % kPipe == 0, "lists are whole rings of kPipe steps");
 
-// descriptor .y: bit 0 wide step, bit 1 end of sub-tile (sub-tile index in bits 31..9), bit 2 last step of its list,
-// bits 8..3 valid lanes of a narrow step
-enum : uint32_t { kFlagWide = 1, kFlagEnd = 2, kFlagLast = 4 };  // kFlagLast: last step of a produced list
-constexpr int kCntShift = 3, kSubIdxShift = 9;
+// descriptor .y: bits 5..0 valid lanes of a narrow step, bit 6 end of sub-tile (sub-tile index in bits 30..8), bit 7 last
+// step of its list, bit 31 wide step (the sign bit: one ISETP tests it)
+enum : uint32_t { kFlagWide = 0x80000000u, kFlagEnd = 0x40, kFlagLast = 0x80 };  // kFlagLast: last step of a produced list
+constexpr int kCntShift = 0, kSubIdxShift = 8;
 
 // rings first (the block is re-aligned to 1 KB inside the kernel so a ring slot is `base | offset`), then the tiles
 __host__ __device__ inline size_t lean_smem_bytes(int nw) { return (size_t)nw * (kTileWords * 4 + kRing * 8) + 1024; }
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
         constexpr int kOddBit = 1 << 30;
         auto issue = [&](const uint2 ds, StepBuf &b) {
             b.meta = ds.y;
-            if (ds.y & kFlagWide) {  // the same word in every lane: a uniform branch, cheaper than a vote + guard
+            if ((int32_t)ds.y < 0) {  // wide flag; the same word in every lane: a uniform branch, cheaper than a vote + guard
                 const unsigned char *p = wide_base + ((size_t)ds.x << 3);
 #if PR_LEAN_L2HINT
                 b.d = ldg_hint_u4(p, l2_keep);
@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                 // pair into (d.x, w.x) made ptxas copy the words right behind the load: a full L2 latency stall per
                 // step; two 32-bit loads avoid that too but cost two extra L1TEX wavefronts per step.)
                 uint2 v = make_uint2(dummy_off, 0u);
-                if ((uint32_t)lane < ((ds.y >> kCntShift) & 63u)) {
+                if ((uint32_t)lane < (ds.y & 63u)) {
                     const unsigned char *p = narrow_base + ((size_t)ds.x << 3);
 #if PR_LEAN_L2HINT >= 2
                     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;"
@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
         // fp32 rounding, so -v is bit-identical to the plain sum) and only the END of an odd epoch re-zeroes the tile.
         auto rmw = [&](const StepBuf &b, auto odd_c) {
             constexpr bool ODD = decltype(odd_c)::value;
-            if (b.meta & kFlagWide) {
+            if ((int32_t)b.meta < 0) {
                 const uint32_t oo[4] = {b.d.x, b.d.y, b.d.z, b.d.w};
                 const float ww[4] = {b.w.x, b.w.y, b.w.z, b.w.w};
                 float v[4];

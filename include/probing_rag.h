@@ -53,10 +53,13 @@ typedef struct pr_bm25_tuning {
                                without a cold stream) */
     int32_t min_items;      /* doc ranges are split until a launch has this many work items   */
     int32_t cand_cap;       /* candidate buffer entries per CTA (mode 2)                      */
-    /* warp-autonomous kernel (modes 3 = scan select, 4 = threshold-on-update select) */
-    int32_t subs_per_item;  /* consecutive 2048-document sub-tiles one warp scores for one query */
-    int32_t warps_per_cta;  /* 4, 8, 9, 12, 13 or 16 (modes 5/6: 4, 8 or 12)                    */
-    int32_t docs_per_launch;/* document range one launch covers for large batches (L2 reuse)   */
+    /* warp-autonomous kernels (modes 3..8) */
+    int32_t subs_per_item;  /* consecutive 2048-document sub-tiles one warp scores for one query (default 24; halved
+                               automatically for batches too small to fill the GPU with items) */
+    int32_t warps_per_cta;  /* 4, 8, 9, 12, 13 or 16 (modes 5..8: 4, 8, 10 or 12)               */
+    int32_t docs_per_launch;/* document range one launch covers for large batches (default 393216: the slice stays
+                               L2-resident; large batches ramp up to it from a one-chunk launch, small batches
+                               get launches of at least 32k work items instead) */
     int32_t lazy_zero;      /* 1 = epoch-tagged accumulators, re-zeroed every 7th sub-tile; 2 = off */
     int32_t rescore_cost;   /* mode 7 planner: cost of rescoring one candidate, in postings (default 64) */
 } pr_bm25_tuning_t;

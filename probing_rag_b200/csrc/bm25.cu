@@ -560,7 +560,7 @@ Layout make_layout(const pr_index *ix, int32_t B, int32_t K)
     // GPU) starts with a SMALL launch and doubles -- c0, c0, 2 c0, 4 c0, ... up to C chunks -- which keeps the share
     // of documents scored without a useful threshold small even on a short shard (8 GPUs: 2.6M documents each).
     {
-        int64_t c0 = B > 0 ? (16384 + (int64_t)B - 1) / B : l.C;
+        int64_t c0 = B > 0 ? (4096 + (int64_t)B - 1) / B : l.C;
         if (c0 < 1) c0 = 1;
         if (c0 > l.C || t.mode < 3) c0 = l.C;
         int pos = 0, cl = (int)c0;

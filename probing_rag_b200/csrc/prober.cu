@@ -36,7 +36,8 @@ constexpr int kStages = 2;
 constexpr int kAStageBytes = kBM * kBK * 2;    // 16 KB
 constexpr int kBStageBytes = kBNH * kBK * 2;   // 32 KB
 constexpr int kStageBytes = 2 * kAStageBytes + 2 * kBStageBytes;  // A_hi A_lo B_hi B_lo = 96 KB
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;  // warps 0-2: TMA / MMA / TMEM alloc, warp 3 idle, warps 4-11: epilogue
+constexpr int kEpiThreads = 256;   // two epilogue threads per row: columns [0,256) and [256,512)
 constexpr float kLnEps = 1e-5f;
 
 // ------------------------------------------------------------------------------ PTX wrappers
@@ -220,7 +221,7 @@ struct GemmArgs {
     int n_probers;
 };
 
-constexpr size_t kGemmSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 5 * kHidden * 4 + 256;
+constexpr size_t kGemmSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 5 * kHidden * 4 + 256 + 4 * kEpiThreads * 4;
 
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -239,6 +240,7 @@ prober_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     uint64_t *empty_bar = full_bar + kStages;                               // [kStages]
     uint64_t *acc_bar = empty_bar + kStages;                                // accumulator complete
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_bar + 1);
+    float *s_red = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(full_bar) + 256);  // [4][kEpiThreads] row partials
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p = blockIdx.y;                 // prober
@@ -257,7 +259,7 @@ prober_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     if (warp == 2) tmem_alloc(tmem_slot, 512);
     if (warp >= 4) {  // epilogue parameters of this prober
         const int t = threadIdx.x - 128;
-        for (int i = t; i < kHidden; i += 128) {
+        for (int i = t; i < kHidden; i += kEpiThreads) {
             s_bias[i] = g.bias[(size_t)p * kHidden + i];
             s_lnw[i] = g.ln_w[(size_t)p * kHidden + i];
             s_lnb[i] = g.ln_b[(size_t)p * kHidden + i];
@@ -310,16 +312,21 @@ prober_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         }
         umma_commit(acc_bar);            // accumulator complete
     } else if (warp >= 4) {
-        // ===== epilogue: thread t owns row row0+t = TMEM lane t
+        // ===== epilogue: TMEM lane t = row row0+t is shared by two threads (warps w and w+4 see the same lane
+        // quadrant): thread (half, t) owns columns [half*256, half*256+256) and the row statistics are combined
+        // through shared memory (always half 0 + half 1, so both threads hold identical values)
         mbar_wait(acc_bar, 0);
         tc_fence_after();
-        const int t = threadIdx.x - 128;
+        const int et = threadIdx.x - 128;
+        const int half = et >> 7, t = et & 127;
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         const int row = row0 + t;
+        const int cb = half * (kHidden / 2), ce = cb + kHidden / 2;
+        auto epi_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); };
         uint32_t r[32];
         // pass 1: bias + SiLU, keep the activations in TMEM, row sum
         float sum = 0.f;
-        for (int c0 = 0; c0 < kHidden; c0 += 32) {
+        for (int c0 = cb; c0 < ce; c0 += 32) {
             tmem_ld32(taddr + c0, r);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -329,10 +336,12 @@ prober_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             }
             tmem_st32(taddr + c0, r);
         }
-        const float mean = sum * (1.f / kHidden);
+        s_red[et] = sum;
+        epi_sync();
+        const float mean = (s_red[t] + s_red[128 + t]) * (1.f / kHidden);
         // pass 2: centred second moment (torch.nn.LayerNorm: biased variance)
         float sq = 0.f;
-        for (int c0 = 0; c0 < kHidden; c0 += 32) {
+        for (int c0 = cb; c0 < ce; c0 += 32) {
             tmem_ld32(taddr + c0, r);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -340,10 +349,12 @@ prober_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 sq += d * d;
             }
         }
-        const float rstd = rsqrtf(sq * (1.f / kHidden) + kLnEps);
+        s_red[kEpiThreads + et] = sq;
+        epi_sync();
+        const float rstd = rsqrtf((s_red[kEpiThreads + t] + s_red[kEpiThreads + 128 + t]) * (1.f / kHidden) + kLnEps);
         // pass 3: normalise; EPI 1 writes the split bf16 operand of fc2, EPI 2 applies fc3 + softmax
         float z0 = 0.f, z1 = 0.f;
-        for (int c0 = 0; c0 < kHidden; c0 += 32) {
+        for (int c0 = cb; c0 < ce; c0 += 32) {
             tmem_ld32(taddr + c0, r);
             if (EPI == 1) {
                 uint32_t hp[16], lp[16];  // bf16 pairs
@@ -375,19 +386,24 @@ prober_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 }
             }
         }
-        if (EPI == 2 && row < g.n_rows) {
-            z0 += g.b3[p * 2 + 0];
-            z1 += g.b3[p * 2 + 1];
-            const size_t o = ((size_t)row * g.n_probers + p) * 2;
-            if (g.logits) {
-                g.logits[o] = z0;
-                g.logits[o + 1] = z1;
+        if (EPI == 2) {
+            s_red[2 * kEpiThreads + et] = z0;
+            s_red[3 * kEpiThreads + et] = z1;
+            epi_sync();
+            if (half == 0 && row < g.n_rows) {
+                z0 = (s_red[2 * kEpiThreads + t] + s_red[2 * kEpiThreads + 128 + t]) + g.b3[p * 2 + 0];
+                z1 = (s_red[3 * kEpiThreads + t] + s_red[3 * kEpiThreads + 128 + t]) + g.b3[p * 2 + 1];
+                const size_t o = ((size_t)row * g.n_probers + p) * 2;
+                if (g.logits) {
+                    g.logits[o] = z0;
+                    g.logits[o + 1] = z1;
+                }
+                const float m = fmaxf(z0, z1);
+                const float e0 = expf(z0 - m), e1 = expf(z1 - m);
+                const float inv = 1.f / (e0 + e1);
+                g.probs[o] = e0 * inv;
+                g.probs[o + 1] = e1 * inv;
             }
-            const float m = fmaxf(z0, z1);
-            const float e0 = expf(z0 - m), e1 = expf(z1 - m);
-            const float inv = 1.f / (e0 + e1);
-            g.probs[o] = e0 * inv;
-            g.probs[o + 1] = e1 * inv;
         }
         tc_fence_before();
     }

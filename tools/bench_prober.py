@@ -34,6 +34,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=16384)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "prober_bench.json"))
+    ap.add_argument("--with-bm25", action="store_true", help="also time the whole config-4 step on the full-size index")
+    ap.add_argument("--n-docs", type=int, default=21015324)
     args = ap.parse_args()
     dev = torch.device("cuda")
     sds = [po.make_prober_state(l) for l in po.PROBE_LAYERS]
@@ -69,6 +71,19 @@ def main():
            "issued_tflops_bf16x3": 3 * flops / ms_fused / 1e9, "peak_tflops_sustained": peak,
            "frac_algorithmic": flops / ms_fused / 1e9 / peak, "frac_issued": 3 * flops / ms_fused / 1e9 / peak,
            "max_abs_dprob_vs_torch_fp32": dp, "retrieve_rate": float(out.retrieve.float().mean().item())}
+    if args.with_bm25:
+        # BASELINE config 4 end to end on the device: hidden states -> prober -> gate -> compaction -> BM25 top-10 of
+        # the queries that retrieve, over the 21M-passage synthetic index
+        import bench
+        from probing_rag_b200 import BM25Retriever
+        from probing_rag_b200.prober import gate_and_retrieve
+        gi, qi, qt = bench.build_workload(args.n_docs, 1 << 22, args.rows, dev)
+        retr = BM25Retriever.from_defaults(index=gi, similarity_top_k=10)
+        d_qi, d_qt = torch.from_numpy(qi).to(dev), torch.from_numpy(qt).to(dev)
+        ms_cfg4 = timeit(lambda: gate_and_retrieve(gate, retr, x, d_qi, d_qt), reps=3, warm=2)
+        n_ret = int(gate(x).retrieve.sum().item())
+        rec.update({"config4_ms": ms_cfg4, "config4_queries_per_s": args.rows / ms_cfg4 * 1e3, "config4_retrieving_queries": n_ret,
+                    "config4_n_docs": args.n_docs, "prober_share_of_config4": ms_fused / ms_cfg4})
     print(json.dumps(rec))
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:

@@ -525,7 +525,7 @@ struct Layout {
     int n_chunks, C, L;
     int G;  // sub-tiles per work item actually used (warp modes): tuning.subs_per_item, halved for small batches
     std::vector<int> launch_chunk0, launch_chunks;  // launch li covers chunks [chunk0, chunk0 + chunks)
-    size_t off_status, off_counters, off_theta, off_plan_theta, off_plan_mask, off_plan_m, off_run_s, off_run_d, off_part_s, off_part_d, total;
+    size_t off_status, off_counters, off_theta, off_plan_theta, off_plan_mask, off_plan_m, off_run_s, off_run_d, off_part_s, off_part_d, off_cursors, total;
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -584,6 +584,9 @@ Layout make_layout(const pr_index *ix, int32_t B, int32_t K)
     l.off_run_d = o;    o = align_up(o + (size_t)B * K * 4, 256);
     l.off_part_s = o;   o = align_up(o + (size_t)B * l.C * K * 4, 256);
     l.off_part_d = o;   o = align_up(o + (size_t)B * l.C * K * 4, 256);
+    // lean kernel: posting cursors of long queries, kCursorCap per resident warp (at most 32 warps per SM)
+    l.off_cursors = o;
+    if (t.mode == 8) o = align_up(o + (size_t)ix->num_sms * 32 * prl::kCursorCap * prl::kCursorWords * 4, 256);
     l.total = o;
     return l;
 }
@@ -1125,6 +1128,7 @@ extern "C" int pr_bm25_topk(pr_index_t *index, int32_t n_queries, const int64_t 
     w.hot_stream = index->hot_stream;
     w.stream_base = index->cold_stream;
     w.hot_base_g = index->hot_base_g;
+    w.cursors = lean_mode ? (uint32_t *)(ws + l.off_cursors) : nullptr;
     w.term_maxw = index->term_maxw;
     w.plan_mask = plan_mask;
     w.plan_m = plan_m;

@@ -60,6 +60,8 @@ using prf::sts_f32;
 constexpr int kRing = 128;    // step descriptors in the per-warp ring (two lists + the trailing no-ops)
 constexpr int kListCap = 60;  // longest list one producer call lays out
 constexpr int kPipe = PR_LEAN_PIPE;
+constexpr int kCursorCap = 1024;  // query terms whose posting cursors fit a warp's scratch (longer queries search per sub-tile)
+constexpr int kCursorWords = 5;   // scratch words per term: cursor + (list start lo/hi, class|row, df)
 static_assert(2 * kListCap + kPipe <= kRing, "ring too small");
 static_assert(kListCap % kPipe == 0, "lists are whole rings of kPipe steps");
 
@@ -191,6 +193,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
         // sub-tile's (several passes) document range, relative to t_b0; t_nd = document at t_pos
         int32_t t_pos = 0, t_le = 0, t_nd = 0x7fffffff;
 
+        int32_t t_df = 0;  // df of the lane's term (set by load_info; used when the cursors are set up)
         auto load_info = [&](int p0, int np, int dlo, int dhi) {
             t_class = -1;
             t_b0 = 0;
@@ -199,6 +202,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
             t_le = 0;
             t_nd = 0x7fffffff;
             int32_t df = 0;
+            t_df = 0;
             if (lane < np) {
                 const int32_t t = a.q_terms[qb + p0 + lane];
                 if (t < 0 || t >= a.n_terms) {
@@ -218,6 +222,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                     }
                 }
             }
+            t_df = df;
             const bool rare = t_class == 0 && df > 0;
             unsigned sm = __ballot_sync(PR_FULL_MASK, rare);
             while (sm) {  // locate [dlo, dhi) in the list by a warp-collective search
@@ -238,6 +243,44 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
         };
 
         if (single && nq > 0) load_info(0, nq, sub0 << kSubShift, min(sub1 << kSubShift, a.n_docs));
+        // Queries of more than 32 terms (LM transcripts, exp_rag.py:428) take several 32-term passes per sub-tile.
+        // Resolving every term of every pass in every sub-tile from scratch (term id -> indptr -> row tables, then a
+        // search for every rare term) cost ~300 us per (query, sub-tile).  Instead each term's static description and
+        // a CURSOR (its next unconsumed posting) live in this warp's global scratch: written once per item here, read
+        // back with one coalesced load per pass, the cursor advanced by a short forward scan per sub-tile.
+        uint32_t *const cur_w = a.cursors ? a.cursors + (size_t)(blockIdx.x * NW + warp) * (kCursorCap * kCursorWords) : nullptr;
+        uint4 *const info_w = reinterpret_cast<uint4 *>(cur_w + kCursorCap);
+        const bool multi = !single && cur_w != nullptr && nq <= kCursorCap;
+        if (multi) {
+            const int item_lo = sub0 << kSubShift, item_hi = min(sub1 << kSubShift, a.n_docs);
+            for (int p0 = 0; p0 < nq; p0 += 32) {
+                load_info(p0, min(32, nq - p0), item_lo, item_hi);
+                if (p0 + lane < nq) {
+                    cur_w[p0 + lane] = (uint32_t)t_pos;
+                    info_w[p0 + lane] = make_uint4((uint32_t)t_b0, (uint32_t)((uint64_t)t_b0 >> 32),
+                                                   ((uint32_t)(t_class + 1) << 28) | ((uint32_t)t_row & 0x0fffffffu), (uint32_t)t_df);  // (row is -1 for rare terms)
+                }
+            }
+        }
+        auto load_cached = [&](int p0, int np) {  // the pass's 32 terms from the scratch
+            t_class = -1;
+            t_b0 = 0;
+            t_row = 0;
+            t_pos = 0;
+            t_le = 0;
+            t_nd = 0x7fffffff;
+            if (lane < np) {
+                const uint4 w = info_w[p0 + lane];
+                t_class = (int)(w.z >> 28) - 1;
+                t_row = (int32_t)(w.z & 0x0fffffffu);
+                t_b0 = (int64_t)(((uint64_t)w.y << 32) | w.x);
+                if (t_class == 0 && w.w > 0u) {
+                    t_le = (int32_t)w.w;  // the list's end: the forward scan stops at the sub-tile's last document anyway
+                    t_pos = (int32_t)cur_w[p0 + lane];
+                    if (t_pos < t_le) t_nd = __ldg(a.doc_ids + t_b0 + t_pos);
+                }
+            }
+        };
 
         // ---- producer: the next list of step descriptors of this item, in (sub-tile, pass, chunk) order
         int it_g = nq > 0 ? sub0 : sub1, it_p0 = 0, it_w0 = 0;
@@ -282,7 +325,8 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                 if (it_w0 == 0) {  // new (sub-tile, pass): what each term has inside this sub-tile
                     const int sub_lo = g << kSubShift;
                     const int sub_hi = sub_lo + min(kSub, a.n_docs - sub_lo);
-                    if (!single) load_info(it_p0, min(32, nq - it_p0), sub_lo, sub_hi);
+                    if (multi) load_cached(it_p0, min(32, nq - it_p0));
+                    else if (!single) load_info(it_p0, min(32, nq - it_p0), sub_lo, sub_hi);
                     uint32_t sb = 0, se = 0;
                     int32_t scan_e = 0;
                     bool unresolved = false;
@@ -300,7 +344,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                             if (g + 2 <= a.n_sub) tb_next = __ldg(tab + 2);
                         }
                     } else if (t_class == 0) {
-                        if (!single) {
+                        if (!single && !multi) {
                             sb = (uint32_t)t_pos;  // located for exactly this sub-tile
                             se = (uint32_t)t_le;
                         } else if (t_nd < sub_hi) {  // cursor: the term has a posting in this sub-tile
@@ -338,6 +382,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                         }
                     }
                     if (unresolved) t_nd = t_pos < t_le ? __ldg(a.doc_ids + t_b0 + t_pos) : 0x7fffffff;
+                    if (multi && t_class == 0 && t_le > 0) cur_w[it_p0 + lane] = (uint32_t)t_pos;
                     seg_x = sb;
                     seg_len = (int32_t)(se - sb);
                 }

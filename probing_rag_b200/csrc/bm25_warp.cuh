@@ -47,6 +47,7 @@ struct WarpArgs {
     const unsigned char *__restrict__ hot_stream;
     const unsigned char *__restrict__ stream_base;  // lean kernel: cold stream (8-byte granule p = CSR posting p), hot stream behind it
     uint32_t hot_base_g;                    // granule index of the hot stream's first byte relative to stream_base
+    uint32_t *cursors;                      // lean kernel: per-warp scratch of kCursorCap * kCursorWords words (long queries), or null
     const float *__restrict__ term_maxw;    // [n_terms] largest weight of the term's list (mode 7), or null
     const uint32_t *__restrict__ plan_mask; // [n_queries] mode 7: bit j = term j of the query is skipped
     const float *__restrict__ plan_m;       // [n_queries] mode 7: upper bound of what the skipped terms add to a document

@@ -20,25 +20,28 @@ def main():
     ap.add_argument("--n-docs", type=int, default=synth.N_DOCS_WIKI)
     ap.add_argument("--vocab", type=int, default=1 << 22)
     ap.add_argument("--batches", default="1,8,64,512,4096")
-    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--k", default="10", help="comma list of depths")
+    ap.add_argument("--kind", default="round0", help="round0 (question-sized queries) or later (LM-transcript-sized, 64..1024 terms)")
     ap.add_argument("--reps", type=int, default=20)
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
-    gi, qi, qt = bench.build_workload(args.n_docs, args.vocab, 4096, dev)
-    for b in [int(x) for x in args.batches.split(",")]:
+    bs = [int(x) for x in args.batches.split(",")]
+    gi, qi, qt = bench.build_workload(args.n_docs, args.vocab, max(bs), dev, query_kind=args.kind)
+    for b, k in [(b, int(k)) for b in bs for k in args.k.split(",")]:
         d_qi = torch.from_numpy(qi[:b + 1]).to(dev)
         d_qt = torch.from_numpy(qt[:qi[b]]).to(dev)
         for _ in range(3):
-            gi.topk(d_qi, d_qt, args.k)
+            gi.topk(d_qi, d_qt, k)
         torch.cuda.synchronize()
+        reps = args.reps if b <= 4096 else 2
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(args.reps):
-            gi.topk(d_qi, d_qt, args.k, check_status=False)
+        for _ in range(reps):
+            gi.topk(d_qi, d_qt, k, check_status=False)
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.reps
-        print(json.dumps({"batch": b, "k": args.k, "ms_per_call": ms, "qps": b / ms * 1e3, "launches": gi.last_launches}), flush=True)
+        ms = e0.elapsed_time(e1) / reps
+        print(json.dumps({"batch": b, "k": k, "kind": args.kind, "terms_per_query": float(qi[b]) / b, "ms_per_call": ms, "qps": b / ms * 1e3, "launches": gi.last_launches}), flush=True)
 
 
 if __name__ == "__main__":

@@ -222,17 +222,21 @@ class BM25Index:
 
     # ------------------------------------------------------------------ queries
     def _workspace(self, n_queries: int, k: int) -> torch.Tensor:
+        """One scratch buffer, grown on demand: gate-compacted batches change size on every call, and the library
+        re-initialises whatever it is handed (any buffer of at least pr_bm25_workspace_bytes works)."""
         key = (n_queries, k)
-        ws = self._ws.get(key)
-        if ws is None:
+        nbytes = self._ws.get(key)
+        if nbytes is None:
             nbytes = int(_lib.lib().pr_bm25_workspace_bytes(self._handle, n_queries, k))
             if nbytes == 0:
                 raise ValueError(f"k must be in [1, {_lib.PR_MAX_K}] (got {k})")
-            if len(self._ws) > 8:
+            if len(self._ws) > 4096:
                 self._ws.clear()
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            self._ws[key] = ws
-        return ws
+            self._ws[key] = nbytes
+        buf = getattr(self, "_ws_buf", None)
+        if buf is None or buf.numel() < nbytes:
+            self._ws_buf = buf = torch.empty(nbytes + nbytes // 4, dtype=torch.uint8, device=self.device)
+        return buf
 
     def topk(self, q_indptr: torch.Tensor, q_terms: torch.Tensor, k: int, out=None, check_status=True):
         """Device CSR query batch -> (scores f32[B,k], doc_ids i32[B,k]) on the device.

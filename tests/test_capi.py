@@ -52,3 +52,17 @@ def test_default_scoring_kernel_resource_budget():
     m = re.search(r"REG:(\d+) STACK:(\d+)", hits[0])
     assert m, hits[0]
     assert int(m.group(1)) <= 80 and int(m.group(2)) <= 48, hits[0]
+
+
+def test_pool_accumulate_argument_errors_without_gpu():
+    """pr_pool_accumulate validates its arguments before any CUDA call."""
+    L = _lib.lib()
+    acc = ctypes.c_void_p(0x1000)
+    act = ctypes.c_void_p(0x2000)
+    assert L.pr_pool_accumulate(None, 4, 6, 0, 2048, act, 0, 4, 1, 2048, 2048, None, None) == _lib.PR_EINVAL
+    assert L.pr_pool_accumulate(acc, 4, 6, 6, 2048, act, 0, 4, 1, 2048, 2048, None, None) == _lib.PR_EINVAL      # slot out of range
+    assert L.pr_pool_accumulate(acc, 4, 6, 0, 2046, act, 0, 4, 1, 2046, 2046, None, None) == _lib.PR_EINVAL      # d_model % 4
+    assert L.pr_pool_accumulate(acc, 4, 6, 0, 2048, act, 3, 4, 1, 2048, 2048, None, None) == _lib.PR_EINVAL      # dtype
+    assert L.pr_pool_accumulate(acc, 4, 6, 0, 2048, act, 0, 5, 1, 2048, 2048, None, None) == _lib.PR_EINVAL      # more rows than the accumulator
+    assert L.pr_pool_accumulate(acc, 4, 6, 0, 2048, act, 1, 4, 1, 2050, 2048, None, None) == _lib.PR_EINVAL      # stride not vectorisable
+    assert L.pr_pool_accumulate(acc, 4, 6, 0, 2048, act, 0, 0, 1, 2048, 2048, None, None) == _lib.PR_OK          # nothing to do

@@ -74,8 +74,8 @@ constexpr int kCntShift = 0, kSubIdxShift = 8;
 __host__ __device__ inline size_t lean_smem_bytes(int nw) { return (size_t)nw * (kTileWords * 4 + kRing * 8) + 1024; }
 
 struct StepBuf {
-    uint4 d;  // tile byte offsets (.x only: narrow)
-    float4 w;
+    uint4 d;   // wide: four tile byte offsets; narrow: (.x, .y) = (tile byte offset, weight bits)
+    float4 w;  // wide: four weights
     uint32_t meta;
 };
 

@@ -442,10 +442,10 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
 
         // ---- fast producer: queries of <= 16 terms whose rare terms have <= 4 postings in the item's range
         // (almost every round-0 query).  The lanes are re-mapped to (sub-tile slot s, term j) = (lane / TPL,
-        // lane % TPL), TPL = 8 or 16, so ONE pass of table look-ups, prefix sums and descriptor stores lays out
+        // lane % TPL), TPL = 4, 8 or 16, so ONE pass of table look-ups, prefix sums and descriptor stores lays out
         // 32 / TPL consecutive sub-tiles; a rare term's few documents sit in registers (tb_cur, tb_next, t_nd,
         // t_le re-used), so there is no cursor.  A sub-tile whose steps overflow the list is cut into chunks.
-        const int tpl_shift = nq <= 8 ? 3 : 4;
+        const int tpl_shift = nq <= 4 ? 2 : nq <= 8 ? 3 : 4;
         const bool fast = single && nq > 0 && nq <= 16 && !__any_sync(PR_FULL_MASK, t_class == 0 && t_le - t_pos > 4);
         if (fast) {
             const int j = lane & ((1 << tpl_shift) - 1);

@@ -542,9 +542,12 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                         write_steps(tl + my_base + pre, 0, n, n_wide);
                         const int pad = my_total - my_t - 1;
                         if (j < pad) sts_u2(slot(tl + my_base + my_t + j), 0u, 0u);
-                        if (j == TPL - 1) sts_u2(slot(tl + my_base + my_total - 1), 0u, (uint32_t)kFlagEnd | ((uint32_t)g << kSubIdxShift));
+                        // the END of the last sub-tile laid out is the list's last step: it carries kFlagLast itself
+                        if (j == TPL - 1)
+                            sts_u2(slot(tl + my_base + my_total - 1), 0u,
+                                   (uint32_t)kFlagEnd | ((uint32_t)g << kSubIdxShift) | (my_base + my_total == base ? (uint32_t)kFlagLast : 0u));
                     }
-                    finish_list(tl + base, base);
+                    finish_list(tl + base, 0);  // (kFlagLast already set above)
                     return base;
                 }
                 // ---- one long sub-tile (g0), a chunk of its steps per call

@@ -28,7 +28,7 @@
 #include "bm25_flat.cuh"
 
 #ifndef PR_LEAN_PIPE
-#define PR_LEAN_PIPE 3
+#define PR_LEAN_PIPE 2
 #endif
 #ifndef PR_LEAN_CTAS
 #define PR_LEAN_CTAS 3

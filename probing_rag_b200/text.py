@@ -14,6 +14,8 @@ from __future__ import annotations
 
 import re
 
+import numpy as np
+
 TOKEN_PATTERN = re.compile(r"(?u)\b\w\w+\b")
 
 # bm25s STOPWORDS_EN (the Lucene/Elasticsearch default list, App. A.2)
@@ -210,39 +212,140 @@ def split_tokens(text: str, stopwords=STOPWORDS_EN) -> list[str]:
     return [t for t in TOKEN_PATTERN.findall(text.lower()) if t not in stopwords]
 
 
+class _AutoId(dict):
+    """surface token -> dense id in first-seen order; `map(d.__getitem__, tokens)` runs in C."""
+
+    def __missing__(self, key):
+        v = self[key] = len(self)
+        return v
+
+
 class Vocabulary:
     """stem -> term id.  bm25s assigns ids from a `set` of stems (hash order, App. A.2); here
-    ids are first-seen order, which changes no score."""
+    ids are first-seen order, which changes no score.
+
+    The corpus side works on batches of documents and numpy arrays (21M passages are ~1.5 G
+    tokens: a Python list of ints would be tens of GB): surface tokens get dense ids through a
+    dict, and one int32 table maps surface id -> stem id (-1 = stop word), so stop-word
+    removal, stemming and the id remap of a whole batch are three numpy gathers."""
 
     def __init__(self, stemmer=None):
         self.stemmer = stemmer if stemmer is not None else get_stemmer()
         self.stem_to_id: dict[str, int] = {}
-        self._surface: dict[str, str] = {}
+        self._surf = _AutoId()                       # surface token -> surface id
+        self._surf_stem = np.zeros(0, np.int32)      # surface id -> stem id, -1 = stop word
+        self._n_mapped = 0
 
     def __len__(self) -> int:
         return len(self.stem_to_id)
 
-    def _stem(self, tok: str) -> str:
-        s = self._surface.get(tok)
-        if s is None:
-            s = self._surface[tok] = self.stemmer.stemWords([tok])[0]
-        return s
+    # ------------------------------------------------------------------ corpus side
+    def _map_new_surfaces(self) -> None:
+        """Stem the surface tokens seen since the last call (each unique token once, in
+        first-seen order, stop words dropped BEFORE stemming -- App. A.2) and extend the table."""
+        n = len(self._surf)
+        if n == self._n_mapped:
+            return
+        if n > self._surf_stem.size:
+            grown = np.full(max(n, 2 * self._surf_stem.size, 1024), -1, np.int32)
+            grown[:self._n_mapped] = self._surf_stem[:self._n_mapped]
+            self._surf_stem = grown
+        new = list(self._surf)[self._n_mapped:] if self._n_mapped else list(self._surf)
+        keep = [i for i, t in enumerate(new) if t not in STOPWORDS_EN]
+        stems = self.stemmer.stemWords([new[i] for i in keep])
+        s2i = self.stem_to_id
+        out = np.full(len(new), -1, np.int32)
+        for i, st in zip(keep, stems):
+            j = s2i.get(st)
+            if j is None:
+                j = s2i[st] = len(s2i)
+            out[i] = j
+        self._surf_stem[self._n_mapped:n] = out
+        self._n_mapped = n
+
+    def encode_corpus_batch(self, texts) -> tuple[np.ndarray, np.ndarray]:
+        """Documents -> (term ids i32[total], doc lengths i32[n]), docs back to back; new
+        stems are added to the vocabulary."""
+        find = TOKEN_PATTERN.findall
+        toks, counts = [], []
+        for t in texts:
+            w = find(t.lower())
+            toks.extend(w)
+            counts.append(len(w))
+        sid = np.fromiter(map(self._surf.__getitem__, toks), dtype=np.int64, count=len(toks))
+        self._map_new_surfaces()
+        stem = self._surf_stem[sid]
+        keep = stem >= 0
+        doc_of = np.repeat(np.arange(len(counts)), counts)
+        lens = np.bincount(doc_of[keep], minlength=len(counts)).astype(np.int32)
+        return stem[keep], lens
+
+    def encode_corpus(self, texts, batch_docs: int = 4096, progress=None) -> tuple[np.ndarray, np.ndarray]:
+        """Stream an iterable of documents through `encode_corpus_batch`; the result is two
+        flat numpy arrays (what `BM25Index.from_tokens` takes), never a Python token list."""
+        tok_parts, len_parts, batch = [], [], []
+        n_done = 0
+
+        def flush():
+            nonlocal n_done
+            t, l = self.encode_corpus_batch(batch)
+            tok_parts.append(t)
+            len_parts.append(l)
+            n_done += len(batch)
+            batch.clear()
+            if progress is not None:
+                progress(n_done)
+
+        for t in texts:
+            batch.append(t)
+            if len(batch) >= batch_docs:
+                flush()
+        if batch:
+            flush()
+        if not tok_parts:
+            return np.zeros(0, np.int32), np.zeros(0, np.int32)
+        return np.concatenate(tok_parts), np.concatenate(len_parts)
 
     def encode_corpus_doc(self, text: str) -> list[int]:
-        ids = []
-        for tok in split_tokens(text):
-            s = self._stem(tok)
-            i = self.stem_to_id.get(s)
-            if i is None:
-                i = self.stem_to_id[s] = len(self.stem_to_id)
-            ids.append(i)
-        return ids
+        return self.encode_corpus_batch([text])[0].tolist()
 
+    # ------------------------------------------------------------------ query side
     def encode_query(self, text: str) -> list[int]:
         """Unknown stems are dropped; order and duplicates kept (App. A.5)."""
         out = []
+        s2i = self.stem_to_id
         for tok in split_tokens(text):
-            i = self.stem_to_id.get(self._stem(tok))
-            if i is not None:
+            sid = self._surf.get(tok)
+            if sid is not None and sid < self._n_mapped:
+                i = int(self._surf_stem[sid])
+            else:   # a surface form the corpus never had may still stem to a known term
+                i = s2i.get(self.stemmer.stemWords([tok])[0], -1)
+            if i >= 0:
                 out.append(i)
         return out
+
+    def encode_queries(self, queries) -> tuple[np.ndarray, np.ndarray]:
+        """Query strings -> CSR batch (q_indptr i64[B+1], q_terms i32[nnz])."""
+        ids = [self.encode_query(q) for q in queries]
+        q_indptr = np.zeros(len(ids) + 1, dtype=np.int64)
+        np.cumsum([len(x) for x in ids], out=q_indptr[1:])
+        q_terms = np.fromiter((t for x in ids for t in x), dtype=np.int32, count=int(q_indptr[-1]))
+        return q_indptr, q_terms
+
+    # ------------------------------------------------------------------ persistence
+    def save(self, path: str) -> None:
+        """One stem per line in term-id order (stems are \\w+ tokens: no newline inside)."""
+        stems = [None] * len(self.stem_to_id)
+        for s, i in self.stem_to_id.items():
+            stems[i] = s
+        with open(path, "w", encoding="utf-8", newline="\n") as f:
+            f.write("\n".join(stems))
+            if stems:
+                f.write("\n")
+
+    @classmethod
+    def load(cls, path: str, stemmer=None) -> "Vocabulary":
+        v = cls(stemmer)
+        with open(path, encoding="utf-8", newline="\n") as f:
+            v.stem_to_id = {line.rstrip("\n"): i for i, line in enumerate(f)}
+        return v

@@ -7,15 +7,23 @@ A step = one pass of the hot path over one batch: all n_queries synthetic querie
 against the whole (doc-sharded for N>1) synthetic corpus and reduced to top-k, including for
 N>1 the NCCL all-gather of the per-shard lists and the merge.  Prints ONE JSON line.
 
-  value        queries/s, inputs resident in HBM, CUDA events, max over ranks
-  e2e          same through the host-buffer API (pinned H2D of the query batch, D2H of the lists)
-  roofline     scoring kernel: algorithmic bytes / its summed device time
-  cpu_baseline the reference's CPU algorithm (oracle port, NumPy like bm25s) on a bounded sample
-  --impl reference   times only that CPU path (all host threads) and prints the same line shape
+  value          queries/s, inputs resident in HBM, CUDA events, max over ranks
+  e2e            same through the host-buffer API (pinned H2D of the query batch, D2H of the lists)
+  roofline       scoring kernel: algorithmic bytes / its summed device time; next to the contractual
+                 HBM fraction, the kernel's real limiter and real DRAM fraction from the committed ncu capture
+  result_digest  sha256 of the final [B,k] (doc ids, scores) of the timed configuration: identical at N = 1, 2, 4, 8
+  sample_digest  sha256 of the lists of the first 32 queries -- printed by BOTH arms (the reference arm computes
+                 them with the CPU oracle in the canonical order), so the driver can see the two arms agree
+  parity_checked queries whose GPU lists were compared (bit-equal ids and scores) with the CPU oracle in this run
+  cpu_baseline   the reference's CPU algorithm on a bounded sample: NumPy port on a thread pool (bm25s n_threads),
+                 plus labelled variants (1 thread = what llama-index runs; threaded C restatement)
+  secondary      BASELINE configs 4 and 5 on the same index (N = 1): prober-gated batch, batch x k x round sweep
+  --impl reference   times only the CPU path (all host threads), never loads libprobingrag.so, same line shape
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -44,12 +52,10 @@ def log(*a):
 from probing_rag_b200.sharding import gather_lists, global_stats, shard_range  # noqa: E402
 
 
-def build_workload(n_docs: int, vocab: int, n_queries: int, device, rank: int = 0, world: int = 1,
-                   query_kind: str = "round0"):
-    """Synthetic Zipf-Mandelbrot corpus shard [lo, hi) built into a BM25Index on `device` with
-    GLOBAL N / avgdl / df, and the seeded query batch (host CSR)."""
-    import torch.distributed as dist
-    from probing_rag_b200 import BM25Index
+def build_arrays(n_docs: int, vocab: int, device, rank: int = 0, world: int = 1):
+    """Synthetic Zipf-Mandelbrot corpus shard [lo, hi) as bm25s-style index arrays on `device`
+    (indptr i64[V+1], doc ids i32[nnz], weights f32[nnz]) with GLOBAL N / avgdl / df.
+    torch library ops only: the reference arm builds its arrays here without touching libprobingrag.so."""
     lo, hi = shard_range(n_docs, rank, world)
     cdf = torch.from_numpy(synth.zipf_mandelbrot_cdf(vocab)).to(device)
     toks, lens = [], []
@@ -82,11 +88,21 @@ def build_workload(n_docs: int, vocab: int, n_queries: int, device, rank: int = 
     del tf, term
     indptr = torch.zeros(vocab + 1, dtype=torch.int64, device=device)
     torch.cumsum(df_local, 0, out=indptr[1:])
-    gi = BM25Index(indptr, doc, w, hi - lo, n_docs, lo, meta={"avgdl": avgdl})
     torch.cuda.synchronize(device)
-    q_indptr, q_terms = synth.queries_np(n_queries, vocab, df_host, kind=query_kind)
-    log(f"[bench] rank {rank}: shard docs [{lo},{hi}) nnz={gi.nnz:,} avgdl={avgdl:.3f} "
-        f"queries={n_queries} ({len(q_terms) / max(n_queries, 1):.2f} terms/query) built in {time.time() - t0:.1f}s")
+    log(f"[bench] rank {rank}: shard docs [{lo},{hi}) nnz={doc.numel():,} avgdl={avgdl:.3f} arrays built in {time.time() - t0:.1f}s")
+    return {"indptr": indptr, "doc_ids": doc, "weights": w, "n_docs": hi - lo, "doc_id_base": lo, "avgdl": avgdl,
+            "df_host": df_host}
+
+
+def build_workload(n_docs: int, vocab: int, n_queries: int, device, rank: int = 0, world: int = 1,
+                   query_kind: str = "round0"):
+    """The shard as a BM25Index on `device` + the seeded query batch (host CSR)."""
+    from probing_rag_b200 import BM25Index
+    a = build_arrays(n_docs, vocab, device, rank, world)
+    gi = BM25Index(a["indptr"], a["doc_ids"], a["weights"], a["n_docs"], n_docs, a["doc_id_base"], meta={"avgdl": a["avgdl"]})
+    torch.cuda.synchronize(device)
+    q_indptr, q_terms = synth.queries_np(n_queries, vocab, a["df_host"], kind=query_kind)
+    gi.df_host = a["df_host"]
     return gi, q_indptr, q_terms
 
 
@@ -135,26 +151,132 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU baseline
-def cpu_reference_qps(host_index: dict, q_indptr, q_terms, k: int, budget_s: float, max_queries: int,
-                      n_threads: int):
-    """The reference's CPU algorithm (bm25s NumPy path, SURVEY App. A.5-A.6: dense f32
-    accumulator, np.add.at per query token, argpartition+argsort) via the oracle port, with
-    bm25s's own thread-pool-over-queries mechanism.  Returns (queries/s, sample size)."""
+N_SAMPLE_DIGEST = 32
+
+
+def digest(ids: np.ndarray, scores: np.ndarray) -> str:
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(ids, dtype=np.int32).tobytes())
+    h.update(np.ascontiguousarray(scores, dtype=np.float32).tobytes())
+    return h.hexdigest()
+
+
+def timed_cpu(fn, host_index, q_indptr, q_terms, k, budget_s, max_queries, n_threads, **kw):
+    """queries/s of `fn(index, q_indptr[:n+1], q_terms, k, n_threads=..)` on as many of the first queries as fit
+    `budget_s` (probed with a few queries first).  Returns (queries/s, n, last result)."""
+    nq = len(q_indptr) - 1
+    n_probe = max(1, min(max(n_threads, 2), nq, max_queries))
+    t0 = time.perf_counter()
+    fn(host_index, q_indptr[:n_probe + 1], q_terms, k, n_threads=n_threads, **kw)
+    dt = time.perf_counter() - t0
+    n = int(min(max_queries, nq, max(n_probe, budget_s / max(dt / n_probe, 1e-9))))
+    t0 = time.perf_counter()
+    res = fn(host_index, q_indptr[:n + 1], q_terms, k, n_threads=n_threads, **kw)
+    dt = time.perf_counter() - t0
+    return n / dt, n, res
+
+
+def cpu_baselines(host_index: dict, q_indptr, q_terms, k: int, budget_s: float, cores: int, nq_total: int):
+    """The reference's CPU algorithm (bm25s NumPy path, SURVEY App. A.5-A.6: dense f32 accumulator, np.add.at
+    per query token, argpartition + argsort) as the oracle restates it, three ways:
+      numpy_pool   thread pool over queries, n_threads = cores   (bm25s's own multi-thread mechanism)  <- headline
+      numpy_1t     one thread                                     (bm25s default n_threads=0: what llama-index runs)
+      c_threads    the plain-C restatement of the same loop, one thread per core (no GIL, no NumPy dispatch)
+    Also returns the canonical oracle lists of the first N_SAMPLE_DIGEST queries (C oracle)."""
     from oracle import bm25_oracle as bo
-    n_probe = min(max(n_threads, 4), len(q_indptr) - 1)
-    t0 = time.perf_counter()
-    bo.retrieve_batch(host_index, q_indptr[:n_probe + 1], q_terms, k, n_threads=n_threads, canonical=False)
-    dt = time.perf_counter() - t0
-    n = int(min(max_queries, len(q_indptr) - 1, max(n_probe, budget_s / max(dt / n_probe, 1e-9))))
-    t0 = time.perf_counter()
-    bo.retrieve_batch(host_index, q_indptr[:n + 1], q_terms, k, n_threads=n_threads, canonical=False)
-    dt = time.perf_counter() - t0
-    return n / dt, n
+    from oracle import c_oracle as co
+    v_pool, n_pool, _ = timed_cpu(bo.retrieve_batch, host_index, q_indptr, q_terms, k, budget_s * 0.5, 512, cores, canonical=False)
+    v_1t, n_1t, _ = timed_cpu(bo.retrieve_batch, host_index, q_indptr, q_terms, k, budget_s * 0.2, 64, 1, canonical=False)
+    v_c, n_c, _ = timed_cpu(co.retrieve_batch, host_index, q_indptr, q_terms, k, budget_s * 0.3, 2048, cores)
+    ns = min(N_SAMPLE_DIGEST, len(q_indptr) - 1)
+    s_s, s_d = co.retrieve_batch(host_index, q_indptr[:ns + 1], q_terms, k, n_threads=cores)
+    what = "of %d queries (first queries of the seeded batch, whole corpus)" % nq_total
+    variants = [
+        {"name": "numpy_pool", "value": v_pool, "unit": UNIT, "cores": cores, "sample": f"{n_pool} {what}",
+         "what": f"NumPy oracle port, thread pool over queries like bm25s n_threads={cores}"},
+        {"name": "numpy_1t", "value": v_1t, "unit": UNIT, "cores": 1, "sample": f"{n_1t} {what}",
+         "what": "NumPy oracle port, one thread: bm25s default n_threads=0, what llama-index's BM25Retriever runs"},
+        {"name": "c_threads", "value": v_c, "unit": UNIT, "cores": cores, "sample": f"{n_c} {what}",
+         "what": "plain-C restatement of the same dense-accumulator loop, one thread per core"},
+    ]
+    base = {"value": v_pool, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_pool} {what}, NumPy oracle port, thread pool over queries like bm25s n_threads={cores}",
+            "variants": variants}
+    return base, (s_s, s_d)
 
 
-def host_copy(gi) -> dict:
-    return {"data": gi.weights.cpu().numpy(), "indices": gi.doc_ids.cpu().numpy(),
-            "indptr": gi.indptr.cpu().numpy(), "num_docs": gi.n_docs, "doc_id_base": gi.doc_id_base}
+def host_arrays(a: dict) -> dict:
+    return {"data": a["weights"].cpu().numpy(), "indices": a["doc_ids"].cpu().numpy(),
+            "indptr": a["indptr"].cpu().numpy(), "num_docs": a["n_docs"], "doc_id_base": a["doc_id_base"]}
+
+
+def make_config(args, world: int, nnz_total: int) -> dict:
+    """The workload description -- the same dict in both arms."""
+    workload = (f"BM25 top-{args.k} over {args.n_docs:,}-passage DPR-Wikipedia-shaped synthetic corpus, "
+                f"{args.n_queries:,} queries" + (f", doc-sharded over {world} GPUs" if world > 1 else ", 1xB200"))
+    return {"workload": workload, "k": args.k, "n_docs": args.n_docs, "n_queries": args.n_queries, "vocab": args.vocab,
+            "nnz": int(nnz_total), "l2": "inputs (postings of %.1f GB) larger than L2" % (nnz_total * 8 / 1e9),
+            "parallelism": f"doc-shard x{world}" if world > 1 else "single"}
+
+
+# ----------------------------------------------------------------------------- secondary: BASELINE configs 4 and 5
+def dev_time(fn, reps: int, warm: int = 2) -> float:
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def secondary_block(gi, qi, qt, device, vocab: int, peaks: dict) -> dict:
+    """BASELINE configs 4 (prober-gated batch of 16,384 questions) and 5 (batch x depth x round sweep, the
+    reference's own regime: small batches, later rounds search with the decoded transcript, exp_rag.py:428)
+    on the index the headline ran on.  Device-timed, inputs resident; a compact table -- the full sweep is
+    committed under profiles/."""
+    from probing_rag_b200.prober import ProberGate, gate_and_retrieve
+    from probing_rag_b200.retriever import BM25Retriever
+    out = {}
+    # ---- config 4
+    rows = 16384
+    sds = [synth.make_prober_state(l) for l in synth.PROBE_LAYERS]
+    gate = ProberGate(sds, device=device)
+    x = synth.make_hidden_states(rows, seed=4).to(device)
+    d_qi = torch.from_numpy(qi[:rows + 1]).to(device)
+    d_qt = torch.from_numpy(qt[:qi[rows]]).to(device)
+    retr = BM25Retriever(None, 10, index=gi)
+    ms_gate = dev_time(lambda: gate(x, sync=False), 10)
+    res = gate_and_retrieve(gate, retr, x, d_qi, d_qt, k=10)
+    n_ret = int(res[0].retrieve.sum().item())
+    ms_all = dev_time(lambda: gate_and_retrieve(gate, retr, x, d_qi, d_qt, k=10), 3, 1)
+    flops = gate.flops(rows)
+    peak_tf = float(peaks.get("bf16_tflops", 1590.0))
+    out["config4_prober_gated_batch"] = {
+        "rows": rows, "retrieve_rows": n_ret, "prober_ms": ms_gate, "prober_rows_per_s": rows / ms_gate * 1e3,
+        "prober_tflops_algorithmic": flops / ms_gate / 1e9, "prober_frac_of_bf16_peak": flops / ms_gate / 1e9 / peak_tf,
+        "prober_peak_tflops": peak_tf, "prober_dtype": "bf16x3 operands, f32 accumulate (tcgen05)",
+        "gate_plus_bm25_top10_ms": ms_all, "questions_per_s": rows / ms_all * 1e3}
+    # ---- config 5
+    sweep = []
+    for b in (1, 8, 64, 512, 4096):
+        for k in (1, 10, 100):
+            bq, bt = d_qi[:b + 1], d_qt[:int(qi[b])]
+            ms = dev_time(lambda: gi.topk(bq, bt, k, check_status=False), 20 if b <= 512 else 3)
+            sweep.append({"round": 0, "batch": b, "k": k, "ms": ms, "qps": b / ms * 1e3,
+                          "alg_gbs": gi.algorithmic_bytes(qi[:b + 1], qt[:qi[b]], k) / ms / 1e6})
+    lqi, lqt = synth.queries_np(64, vocab, gi.df_host, kind="later")       # rounds 1-3: transcript-sized queries
+    d_lqi, d_lqt = torch.from_numpy(lqi).to(device), torch.from_numpy(lqt).to(device)
+    for b in (1, 8, 64):
+        bq, bt = d_lqi[:b + 1], d_lqt[:int(lqi[b])]
+        ms = dev_time(lambda: gi.topk(bq, bt, 10, check_status=False), 5, 1)
+        sweep.append({"round": "1-3 (transcript, %.0f terms/query)" % (lqi[b] / b), "batch": b, "k": 10, "ms": ms, "qps": b / ms * 1e3,
+                      "alg_gbs": gi.algorithmic_bytes(lqi[:b + 1], lqt[:lqi[b]], 10) / ms / 1e6})
+    out["config5_sweep"] = sweep
+    return out
 
 
 # ----------------------------------------------------------------------------- main
@@ -168,8 +290,10 @@ def main():
     ap.add_argument("--vocab", type=int, default=1 << 22)
     ap.add_argument("--n-queries", type=int, default=65536)
     ap.add_argument("--k", type=int, default=10)
-    ap.add_argument("--cpu-budget-s", type=float, default=20.0)
+    ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-exchange", action="store_true", help="N > 1: no threshold exchange between launches (A/B)")
     ap.add_argument("--tune", default="", help="comma list key=value for pr_bm25_tuning_t")
     args = ap.parse_args()
 
@@ -183,63 +307,61 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
-    if world > 1 and args.impl == "ours":
-        dist.init_process_group("nccl", device_id=device)
-    n_gpus = world if args.impl == "ours" else args.gpus
-    workload = (f"BM25 top-{args.k} over {args.n_docs:,}-passage DPR-Wikipedia-shaped synthetic corpus, "
-                f"{args.n_queries:,} queries" + (f", doc-sharded over {world} GPUs" if world > 1 else ", 1xB200"))
     cores = os.cpu_count() or 1
+    nq, k = args.n_queries, args.k
 
     if args.impl == "reference":
-        gi, qi, qt = build_workload(args.n_docs, args.vocab, args.n_queries, device)
-        host = host_copy(gi)
-        del gi
+        # the whole corpus as host arrays (built with torch library ops on the GPU, then dropped from it); the
+        # product library is never loaded in this process
+        a = build_arrays(args.n_docs, args.vocab, device)
+        host = host_arrays(a)
+        nnz = int(a["doc_ids"].numel())
+        qi, qt = synth.queries_np(nq, args.vocab, a["df_host"])
+        del a
         torch.cuda.empty_cache()
-        per_step_budget = max(5.0, min(40.0, 150.0 / max(args.steps + args.warmup, 1)))
+        from oracle import bm25_oracle as bo
+        from oracle import c_oracle as co
+        per_step_budget = max(5.0, min(40.0, 120.0 / max(args.steps + args.warmup, 1)))
         vals, n = [], 0
         for i in range(args.warmup + args.steps):
-            v, n = cpu_reference_qps(host, qi, qt, args.k, per_step_budget, 512, cores)
+            v, n, _ = timed_cpu(bo.retrieve_batch, host, qi, qt, k, per_step_budget, 512, cores, canonical=False)
             if i >= args.warmup:
                 vals.append(v)
         v = float(np.mean(vals))
-        sample = f"{n} of {args.n_queries} queries per step (seeded subsample, whole corpus)"
+        base, (s_s, s_d) = cpu_baselines(host, qi, qt, k, 20.0, cores, nq)
+        base = dict(base, value=v, sample=f"{n} of {nq} queries per step (first queries of the seeded batch, whole corpus), "
+                                           f"NumPy oracle port, thread pool over queries like bm25s n_threads={cores}")
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * n / v,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "k": args.k, "n_docs": args.n_docs, "n_queries": args.n_queries},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": make_config(args, args.gpus, nnz),
+            "cpu_baseline": base,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "sample_digest": digest(s_d, s_s), "sample_queries": int(s_d.shape[0]),
+            "native_library_loaded": "libprobingrag" in open("/proc/self/maps").read(),
             "gpu_launches": 0}))
         return
 
-    from probing_rag_b200 import merge_topk
-    gi, qi, qt = build_workload(args.n_docs, args.vocab, args.n_queries, device, rank, world)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from probing_rag_b200.sharding import ShardedBM25
+    gi, qi, qt = build_workload(args.n_docs, args.vocab, nq, device, rank, world)
     if args.tune:
         gi.set_tuning(**{kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.tune.split(",")})
-    nq, k = args.n_queries, args.k
+    sharded = ShardedBM25(gi, exchange=not args.no_exchange) if world > 1 else None
     d_qi = torch.from_numpy(qi).to(device)
     d_qt = torch.from_numpy(qt).to(device)
     out = (torch.empty((nq, k), dtype=torch.float32, device=device),
            torch.empty((nq, k), dtype=torch.int32, device=device))
-    gath_s = torch.empty((world, nq, k), dtype=torch.float32, device=device) if world > 1 else None
-    gath_d = torch.empty((world, nq, k), dtype=torch.int32, device=device) if world > 1 else None
 
     def step_device():
-        gi.topk(d_qi, d_qt, k, out=out, check_status=False)
         if world > 1:
-            gather_lists(out[0], out[1], out=(gath_s, gath_d))
-            return merge_topk(gath_s, gath_d)
-        return out
+            return sharded.topk(d_qi, d_qt, k, check_status=False)
+        return gi.topk(d_qi, d_qt, k, out=out, check_status=False)
 
     def step_host():
-        s, d, h2d, d2h = gi.topk_host(qi, qt, k)
-        if world > 1:
-            ds, dd = torch.from_numpy(s).to(device), torch.from_numpy(d).to(device)
-            gather_lists(ds, dd, out=(gath_s, gath_d))
-            ms, md = merge_topk(gath_s, gath_d)
-            s, d = ms.cpu().numpy(), md.cpu().numpy()
-        return s, d, h2d, d2h
+        return (sharded if world > 1 else gi).topk_host(qi, qt, k)
 
     def barrier():
         if world > 1:
@@ -265,9 +387,12 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev, _ = timed(step_device, args.steps)
+    ms_dev, res = timed(step_device, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    n_score_launches = gi.num_launches(nq, k)
+    # kernels of ours per step: init + (score + merge) per launch; N > 1: + the merge of the gathered lists
     launches_per_step = gi.last_launches + (1 if world > 1 else 0)
+    res_s, res_d = res[0].cpu().numpy(), res[1].cpu().numpy()
 
     # scoring-kernel device time for the roofline (events around its launches)
     gi.set_profiling(True)
@@ -282,22 +407,19 @@ def main():
     for _ in range(2):
         step_host()
     ms_e2e, last = timed(step_host, args.steps)
-    _, _, h2d, d2h = last
+    e2e_s, e2e_d, h2d, d2h = last
+    assert np.array_equal(e2e_d, res_d) and np.array_equal(e2e_s, res_s), "host-buffer path returned different lists"
 
-    # size-independent sanity on the measured output (not a parity claim; tests/ hold those)
-    res = step_device()
-    torch.cuda.synchronize(device)
-    s_chk = res[0]
-    assert bool((s_chk[:, :-1] >= s_chk[:, 1:]).all()), "ranked lists not score-descending"
+    # size-independent properties of the measured output: ranked, canonical tie order, ids in range
+    assert bool((res_s[:, :-1] >= res_s[:, 1:]).all()), "ranked lists not score-descending"
+    tie = res_s[:, :-1] == res_s[:, 1:]
+    assert bool((res_d[:, :-1][tie] < res_d[:, 1:][tie]).all()), "ties not in ascending doc id order"
+    assert int(res_d.min()) >= 0 and int(res_d.max()) < args.n_docs
 
+    t = torch.tensor([float(alg_bytes), float(gi.nnz)], dtype=torch.float64, device=device)
     if world > 1:
-        t = torch.tensor([alg_bytes, score_ms * 1e3], dtype=torch.float64, device=device)
-        mx = t.clone()
-        dist.all_reduce(t)                       # total algorithmic bytes over shards
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        alg_total = float(t[0].item())
-    else:
-        alg_total = float(alg_bytes)
+        dist.all_reduce(t)                       # total algorithmic bytes / postings over the shards
+    alg_total, nnz_total = float(t[0].item()), int(t[1].item())
 
     if rank != 0:
         if world > 1:
@@ -309,17 +431,13 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    tuning = gi.get_tuning()
-    kernel = {1: "bm25_score_kernel", 2: "bm25_score_kernel", 3: "bm25_warp_kernel", 4: "bm25_warp_kernel",
-              8: "bm25_lean_kernel" if gi.aux_info().get("lean_ok") else "bm25_flat_kernel"}.get(
-        tuning["mode"], "bm25_flat_kernel")
-    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/), if any
-    traffic, traffic_src = None, None
+    kernel = "bm25_lean_kernel"
+    # what the committed `ncu --set full` capture of that kernel says (profiles/): DRAM bytes, real limiter
+    cap = {}
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if tj.get("kernel") == kernel:
-            traffic = int(tj["dram_bytes_per_launch"])
-            traffic_src = tj.get("source")
+        cap = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if cap.get("kernel") != kernel:
+            cap = {}
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
@@ -327,29 +445,52 @@ def main():
     achieved = alg_bytes / (score_ms * 1e-3) / 1e9 if score_ms > 0 else 0.0
     value = nq * args.steps / (ms_dev * 1e-3)
     e2e = nq * args.steps / (ms_e2e * 1e-3)
+    traffic = int(cap["dram_bytes_per_launch"]) if "dram_bytes_per_launch" in cap else None
+    dram_frac = None
+    if traffic and cap.get("captured_launch_ms"):
+        dram_frac = traffic / (cap["captured_launch_ms"] * 1e-3) / 1e9 / peak
 
-    cpu_base = None
-    if not args.no_cpu_baseline and world == 1:
-        host = host_copy(gi)
-        v, n = cpu_reference_qps(host, qi, qt, k, args.cpu_budget_s, 512, cores)
-        cpu_base = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                    "sample": f"{n} of {nq} queries (seeded subsample, whole corpus), NumPy oracle port, "
-                              f"thread pool over queries like bm25s n_threads={cores}"}
+    cpu_base, parity = None, {"parity_checked": 0}
+    sample_dig = None
+    if world == 1 and not args.no_cpu_baseline:
+        host = {"data": gi.weights.cpu().numpy(), "indices": gi.doc_ids.cpu().numpy(), "indptr": gi.indptr.cpu().numpy(),
+                "num_docs": gi.n_docs, "doc_id_base": gi.doc_id_base}
+        cpu_base, (o_s, o_d) = cpu_baselines(host, qi, qt, k, args.cpu_budget_s, cores, nq)
+        ns = o_d.shape[0]
+        ok = bool(np.array_equal(o_d, res_d[:ns]) and np.array_equal(o_s, res_s[:ns]))
+        parity = {"parity_checked": int(ns), "parity_ok": ok,
+                  "parity_what": "GPU lists of the first queries == CPU oracle (C restatement, canonical order): ids and f32 scores bit-equal"}
+        assert ok, "GPU lists differ from the CPU oracle on the checked sample"
+        del host
+    ns = min(N_SAMPLE_DIGEST, nq)
+    sample_dig = digest(res_d[:ns], res_s[:ns])
+
+    secondary = None
+    if world == 1 and not args.no_secondary:
+        try:
+            secondary = secondary_block(gi, qi, qt, device, args.vocab, peaks)
+        except Exception as ex:                               # the headline line must not die on the side table
+            secondary = {"error": repr(ex)}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload, "k": k, "n_docs": args.n_docs, "n_queries": nq, "vocab": args.vocab,
-                   "nnz_shard0": gi.nnz, "l2": "inputs (index shard of %.1f GB) larger than L2" % (gi.nnz * 8 / 1e9),
-                   "tuning": tuning, "parallelism": f"doc-shard x{world}" if world > 1 else "single"},
+        "config": make_config(args, world, nnz_total),
+        "plan": {"tuning": gi.get_tuning(), "scoring_launches_per_step": n_score_launches, "nnz_shard0": gi.nnz,
+                 "threshold_exchange": bool(world > 1 and not args.no_exchange)},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches_per_step * args.steps),
+        "result_digest": digest(res_d, res_s), "sample_digest": sample_dig, "sample_queries": int(ns),
+        **parity,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "frac_of_8000_nominal": achieved / 8000.0, "traffic": traffic,
-                     "traffic_unit": "DRAM bytes (read + write) per launch, ncu", "traffic_source": traffic_src,
+                     "traffic_unit": "DRAM bytes (read + write) per launch, ncu", "traffic_source": cap.get("source"),
+                     "bound_note": "contractual accounting (algorithmic posting bytes / kernel time vs copy bandwidth); a 64k-query "
+                                   "batch re-reads each launch's posting slice from L2, so the chip-level limiter is not DRAM",
+                     "limiter": cap.get("limiter"), "dram_frac": dram_frac,
                      "peak_source": peak_src, "kernel": kernel,
                      "algorithmic_bytes_per_launch": int(alg_bytes / max(score_launches, 1)),
                      "algorithmic_bytes_per_step_rank0": int(alg_bytes),
@@ -357,6 +498,7 @@ def main():
                      "kernel_ms_per_step": score_ms, "kernel_launches_per_step": score_launches,
                      "kernel_share_of_step": score_ms / (ms_dev / args.steps)},
         "cpu_baseline": cpu_base,
+        "secondary": secondary,
     }
     print(json.dumps(line))
     if world > 1:

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PR_VERSION 100 /* 0.1.0 */
+#define PR_VERSION 200 /* 0.2.0 */
 
 #define PR_OK 0
 #define PR_EINVAL (-1)     /* bad argument (null pointer, k out of range, misaligned buffer) */
@@ -40,28 +40,17 @@ extern "C" {
 typedef struct pr_index pr_index_t;
 typedef void *pr_stream_t; /* cudaStream_t */
 
-/* Tunables of the BM25 scoring kernel; zero fields keep the default. */
+/* Tunables of the BM25 launch plan; zero fields keep the default. */
 typedef struct pr_bm25_tuning {
-    int32_t tile_docs;      /* documents per shared-memory score tile (multiple of 4*threads) */
-    int32_t tiles_per_item; /* consecutive tiles one CTA scores for one query                 */
-    int32_t threads;        /* 256, 512 or 1024                                               */
-    int32_t mode;           /* CTA-cooperative kernel: 1 = scan select, 2 = threshold-on-update; warp-autonomous
-                               segment-loop kernel: 3 = scan select, 4 = threshold-on-update; warp-autonomous
-                               flat-step kernel: 5 = scan select, 6 = threshold-on-update, 7 = 6 + rank-safe
-                               skipping of frequent terms with exact rescoring of the candidates; 8 (default) =
-                               lean-step kernel over the cold + hot posting streams (runs as 6 on an index
-                               without a cold stream) */
-    int32_t min_items;      /* doc ranges are split until a launch has this many work items   */
-    int32_t cand_cap;       /* candidate buffer entries per CTA (mode 2)                      */
-    /* warp-autonomous kernels (modes 3..8) */
-    int32_t subs_per_item;  /* consecutive 2048-document sub-tiles one warp scores for one query (default 24; halved
-                               automatically for batches too small to fill the GPU with items) */
-    int32_t warps_per_cta;  /* 4, 8, 9, 12, 13 or 16 (modes 5..8: 4, 8, 10 or 12)               */
-    int32_t docs_per_launch;/* document range one launch covers for large batches (default 393216: the slice stays
-                               L2-resident; large batches ramp up to it from a one-chunk launch, small batches
-                               get launches of at least 32k work items instead) */
-    int32_t lazy_zero;      /* 1 = epoch-tagged accumulators, re-zeroed every 7th sub-tile; 2 = off */
-    int32_t rescore_cost;   /* mode 7 planner: cost of rescoring one candidate, in postings (default 64) */
+    int32_t subs_per_item;   /* consecutive 2048-document sub-tiles one warp scores for one query (default 24; halved
+                                automatically for batches too small to give every resident warp items_per_warp items) */
+    int32_t warps_per_cta;   /* 4, 8 (default), 10 or 12 */
+    int32_t docs_per_launch; /* document range one launch covers for large batches (default 393216); bounds the
+                                per-item list storage in the workspace ([n_queries][chunks per launch][k] pairs) */
+    int32_t min_items;       /* a launch covers at least this many (query, chunk) work items (default 32768), so a
+                                small batch is ONE scoring launch + one merge */
+    int32_t items_per_warp;  /* small batches: work items per resident warp the plan aims for (default 1:
+                                per-item set-up dominates a single query, measured in profiles/r02) */
 } pr_bm25_tuning_t;
 
 int pr_version(void);
@@ -81,22 +70,28 @@ int pr_index_create(pr_index_t **out, int device, int64_t n_docs_global, int32_t
                     const int32_t *doc_ids_dev, const float *weights_dev);
 int pr_index_destroy(pr_index_t *index);
 
-/* Per-index structures of the warp-autonomous scoring kernels (tuning.mode >= 3), built once per
- * index into caller-owned device memory of pr_index_aux_bytes(index, budget) bytes:
- *   - heavy_row[n_terms] and, for every term whose df exceeds a threshold chosen so the table
- *     fits a fifth of `table_budget_bytes`, the posting offset of each 2048-document boundary;
- *   - the hot posting stream (modes 5/6): for the terms with >= 8 postings per 2048 documents, as
- *     many as fit the rest of the budget, a padded, bank-aware, mask-free copy of their postings
- *     (about 10 bytes per hot posting).  Without it modes 5/6 read every term from the CSR;
- *   - the cold posting stream (mode 8): every posting as an interleaved (tile byte offset, weight) pair,
- *     8 bytes per posting, which pr_index_aux_bytes adds on top of the budget.  pr_index_lean_info
- *     reports whether mode 8 can use it (the stream space must fit 32-bit granule indices).
+/* Per-index structures of the scoring kernel, built once per index into caller-owned device memory of
+ * pr_index_aux_bytes(index, budget) bytes:
+ *   - the COLD posting stream: every posting as an interleaved (tile byte offset, weight) pair, 8 bytes per posting
+ *     (pr_index_aux_bytes adds it on top of the budget);
+ *   - heavy_row[n_terms] and, for every term whose df exceeds a threshold chosen so the table fits a fifth of
+ *     `table_budget_bytes`, the posting offset of each 2048-document boundary;
+ *   - the HOT posting stream: for the terms with >= 8 postings per 2048 documents, as many as fit the rest of the
+ *     budget and the 32-bit granule space, a padded, bank-aware, mask-free copy of their postings (about 10 bytes
+ *     per hot posting).
  * pr_index_build_aux synchronises `stream`. */
+typedef struct pr_index_aux_info {
+    int32_t table_rows;        /* terms with a boundary table row */
+    int32_t hot_rows;          /* terms in the hot stream */
+    int32_t n_sub_tiles;       /* 2048-document sub-tiles of this shard */
+    int64_t table_min_df;      /* df above which a term is tabulated */
+    int64_t hot_min_df;        /* df from which a term is hot */
+    int64_t hot_stream_bytes;
+    int64_t cold_stream_bytes;
+} pr_index_aux_info_t;
 size_t pr_index_aux_bytes(const pr_index_t *index, size_t table_budget_bytes);
 int pr_index_build_aux(pr_index_t *index, void *aux_dev, size_t aux_bytes, pr_stream_t stream);
-int pr_index_aux_info(const pr_index_t *index, int32_t *n_rows, int64_t *min_df);
-int pr_index_lean_info(const pr_index_t *index, int32_t *lean_ok, int64_t *cold_bytes);
-int pr_index_hot_info(const pr_index_t *index, int32_t *n_hot, int64_t *min_df, int64_t *stream_bytes);
+int pr_index_aux_info(const pr_index_t *index, pr_index_aux_info_t *info);
 int pr_index_set_tuning(pr_index_t *index, const pr_bm25_tuning_t *tuning);
 int pr_index_get_tuning(const pr_index_t *index, pr_bm25_tuning_t *tuning);
 
@@ -105,17 +100,36 @@ size_t pr_bm25_workspace_bytes(const pr_index_t *index, int32_t n_queries, int32
 
 /* Batched BM25Retriever.retrieve (/root/reference/exp_rag.py:426, 428, 492; utils.py:640;
  * bm25s.BM25.retrieve + selection.topk) at token-id level.
- *   q_indptr_dev int64[n_queries+1], q_terms_dev int32[nnzq]: CSR batch of query term ids in
+ *   q_indptr_dev int64[n_queries+1], q_terms_dev int32[n_q_terms]: CSR batch of query term ids in
  *   query-token order, duplicates kept.  Scores are accumulated in fp32 in that order, one
  *   rounded add per posting, exactly as the reference's dense accumulator does.
  *   out_scores_dev float[n_queries*k], out_doc_ids_dev int32[n_queries*k] (GLOBAL doc ids).
  * Fewer than k positive scores: the tail is filled with this shard's lowest doc ids at
- * score 0.0.  A term id outside [0, n_terms) is skipped and flagged: pr_bm25_status() reports
- * PR_ERANGE after the stream is synchronised. */
+ * score 0.0.  Both arrays are validated ON THE DEVICE, nothing is read out of bounds: a q_indptr that
+ * does not start at 0, decreases or points past n_q_terms makes the call score nothing and
+ * pr_bm25_status() report PR_EINVAL; a term id outside [0, n_terms) is skipped and reported as
+ * PR_ERANGE (bm25s raises ValueError there, App. A.5). */
 int pr_bm25_topk(pr_index_t *index, int32_t n_queries, const int64_t *q_indptr_dev,
-                 const int32_t *q_terms_dev, int32_t k, float *out_scores_dev,
+                 const int32_t *q_terms_dev, int64_t n_q_terms, int32_t k, float *out_scores_dev,
                  int32_t *out_doc_ids_dev, void *workspace_dev, size_t workspace_bytes,
                  pr_stream_t stream);
+
+/* The same call cut at launch boundaries, for doc-range shards on several GPUs.  A call
+ * walks its shard in pr_bm25_num_launches() launches.  The workspace holds, at byte offset
+ * pr_bm25_theta_offset(), float theta[n_queries]: the best known LOWER BOUND of every query's final
+ * k-th score (-1 = none).  The scoring warps read and raise it while they run; between two ranges the
+ * caller may raise it further with what the other shards found -- e.g. an all-reduce(MAX) of that
+ * array over the ranks: the global k-th score is >= every shard's local k-th score, so each shard then
+ * filters with the strongest bound any shard knows and the merged result stays bit-identical.
+ * Ranges must be issued in order, [0, a), [a, b), ... up to the launch count, with the same arguments.
+ * pr_bm25_num_launches: n_docs < 0 = this index; otherwise the count a shard of n_docs documents would have
+ * under this index's tuning (ranks agree on the number of exchange rounds through the longest shard). */
+int32_t pr_bm25_num_launches(const pr_index_t *index, int32_t n_queries, int32_t k, int64_t n_docs);
+size_t pr_bm25_theta_offset(const pr_index_t *index, int32_t n_queries, int32_t k);
+int pr_bm25_topk_range(pr_index_t *index, int32_t n_queries, const int64_t *q_indptr_dev,
+                       const int32_t *q_terms_dev, int64_t n_q_terms, int32_t k, float *out_scores_dev,
+                       int32_t *out_doc_ids_dev, void *workspace_dev, size_t workspace_bytes,
+                       int32_t launch_begin, int32_t launch_end, pr_stream_t stream);
 
 /* Reads the status word pr_bm25_topk left in the workspace (synchronises `stream`). */
 int pr_bm25_status(const void *workspace_dev, pr_stream_t stream);
@@ -162,14 +176,14 @@ typedef struct pr_prober_set {
 
 size_t pr_prober_workspace_bytes(int32_t n_probers, int32_t n_rows, int32_t d_model, int32_t hidden);
 
-/* X_dev float[n_rows, n_probers, d_model]: pooled hidden states, one per probed layer
- * (exp_rag.py:385-386).  Outputs: out_logits_dev float[n_rows, n_probers, 2] (may be NULL),
- * out_probsum_dev float[n_rows, 2] = sum over probers >= ablation of softmax(logits)
- * (exp_rag.py:407-410), out_retrieve_mask_dev uint8[n_rows] (1 = retrieve, i.e. NOT
- * probsum[0] + theta < probsum[1], exp_rag.py:414), out_compact_idx_dev int32[n_rows] (indices
- * of the rows that retrieve, ascending; the first *out_n_retrieve_dev are valid).
- * workspace_dev must be 1024-byte aligned. */
-int pr_prober_forward(const pr_prober_set_t *probers, int32_t n_rows, const float *X_dev, float theta,
+/* X_dev [n_rows, n_probers, d_model]: pooled hidden states, one per probed layer (exp_rag.py:385-386), of
+ * x_dtype 0 = f32, 1 = bf16, 2 = f16 (whatever the LM produced; 16-byte aligned).  Outputs:
+ * out_logits_dev float[n_rows, n_probers, 2] (may be NULL), out_probsum_dev float[n_rows, 2] = sum over
+ * probers >= ablation of softmax(logits) (exp_rag.py:407-410), out_retrieve_mask_dev uint8[n_rows] (1 =
+ * retrieve, i.e. NOT probsum[0] + theta < probsum[1], evaluated in double like the reference's Python floats,
+ * exp_rag.py:414), out_compact_idx_dev int32[n_rows] (indices of the rows that retrieve, ascending; the first
+ * *out_n_retrieve_dev are valid, the rest read -1).  workspace_dev must be 1024-byte aligned. */
+int pr_prober_forward(const pr_prober_set_t *probers, int32_t n_rows, const void *X_dev, int32_t x_dtype, double theta,
                       int32_t ablation, float *out_logits_dev, float *out_probsum_dev,
                       uint8_t *out_retrieve_mask_dev, int32_t *out_compact_idx_dev,
                       int32_t *out_n_retrieve_dev, void *workspace_dev, size_t workspace_bytes,

@@ -19,10 +19,14 @@ c_i32, c_i64, c_f32, c_vp, c_sz = ctypes.c_int32, ctypes.c_int64, ctypes.c_float
 
 
 class Tuning(ctypes.Structure):
-    _fields_ = [("tile_docs", c_i32), ("tiles_per_item", c_i32), ("threads", c_i32),
-                ("mode", c_i32), ("min_items", c_i32), ("cand_cap", c_i32),
-                ("subs_per_item", c_i32), ("warps_per_cta", c_i32), ("docs_per_launch", c_i32),
-                ("lazy_zero", c_i32), ("rescore_cost", c_i32)]
+    _fields_ = [("subs_per_item", c_i32), ("warps_per_cta", c_i32), ("docs_per_launch", c_i32),
+                ("min_items", c_i32), ("items_per_warp", c_i32)]
+
+
+class AuxInfo(ctypes.Structure):
+    _fields_ = [("table_rows", c_i32), ("hot_rows", c_i32), ("n_sub_tiles", c_i32),
+                ("table_min_df", c_i64), ("hot_min_df", c_i64), ("hot_stream_bytes", c_i64),
+                ("cold_stream_bytes", c_i64)]
 
 
 class ProberSet(ctypes.Structure):
@@ -42,13 +46,15 @@ SIGNATURES = {
     "pr_index_destroy": (ctypes.c_int, [c_vp]),
     "pr_index_aux_bytes": (c_sz, [c_vp, c_sz]),
     "pr_index_build_aux": (ctypes.c_int, [c_vp, c_vp, c_sz, c_vp]),
-    "pr_index_aux_info": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i32), ctypes.POINTER(c_i64)]),
-    "pr_index_lean_info": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i32), ctypes.POINTER(c_i64)]),
-    "pr_index_hot_info": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i32), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
+    "pr_index_aux_info": (ctypes.c_int, [c_vp, ctypes.POINTER(AuxInfo)]),
     "pr_index_set_tuning": (ctypes.c_int, [c_vp, ctypes.POINTER(Tuning)]),
     "pr_index_get_tuning": (ctypes.c_int, [c_vp, ctypes.POINTER(Tuning)]),
     "pr_bm25_workspace_bytes": (c_sz, [c_vp, c_i32, c_i32]),
-    "pr_bm25_topk": (ctypes.c_int, [c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "pr_bm25_topk": (ctypes.c_int, [c_vp, c_i32, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "pr_bm25_num_launches": (c_i32, [c_vp, c_i32, c_i32, c_i64]),
+    "pr_bm25_theta_offset": (c_sz, [c_vp, c_i32, c_i32]),
+    "pr_bm25_topk_range": (ctypes.c_int, [c_vp, c_i32, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_sz, c_i32, c_i32,
+                                          c_vp]),
     "pr_bm25_status": (ctypes.c_int, [c_vp, c_vp]),
     "pr_bm25_last_launches": (c_i64, [c_vp]),
     "pr_index_set_profiling": (ctypes.c_int, [c_vp, ctypes.c_int]),
@@ -57,8 +63,8 @@ SIGNATURES = {
     "pr_prober_workspace_bytes": (c_sz, [c_i32, c_i32, c_i32, c_i32]),
     "pr_pool_accumulate": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_i64, c_i64,
                                           c_vp, c_vp]),
-    "pr_prober_forward": (ctypes.c_int, [ctypes.POINTER(ProberSet), c_i32, c_vp, c_f32, c_i32, c_vp, c_vp, c_vp,
-                                         c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "pr_prober_forward": (ctypes.c_int, [ctypes.POINTER(ProberSet), c_i32, c_vp, c_i32, ctypes.c_double, c_i32, c_vp, c_vp,
+                                         c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
 }
 
 _lib = None

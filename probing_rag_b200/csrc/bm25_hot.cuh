@@ -25,7 +25,7 @@
 // pr_index_build_aux into caller-owned memory.
 #pragma once
 
-#include "bm25_warp.cuh"
+#include "bm25_tables.cuh"
 
 namespace prh {
 

@@ -1,15 +1,14 @@
-// Pickers of the templated warp-autonomous scoring kernels.  Each family is instantiated in its own translation
-// unit (bm25_kernels_warp.cu / _flat.cu / _lean.cu) so the ~60 kernel instantiations compile in parallel.
+// Picker of the templated scoring kernel.  The instantiations live in their own translation units
+// (bm25_kernels_lean*.cu) so the library compiles in parallel.
 #pragma once
 
-#include "bm25_warp.cuh"
+#include "bm25_tables.cuh"
 
 namespace prk {
 
-typedef void (*warp_fn_t)(const prw::WarpArgs);
+typedef void (*score_fn_t)(const prw::ScoreArgs);
 
-warp_fn_t pick_warp_fn(int nw, int E, bool lazy);   // segment-loop kernel, tuning.mode 3/4
-warp_fn_t pick_flat_fn(int nw, int E, bool skip);   // flat-step kernel, modes 5/6 (skip: mode 7)
-warp_fn_t pick_lean_fn(int nw, int E);              // lean-step kernel, mode 8
+score_fn_t pick_lean_fn(int nw, int E);   // nw = warps per CTA (4, 8, 10, 12), E = ceil(k / 32) rounded up to 1, 2, 4
+score_fn_t pick_lean_fn_nw8(int E);       // (bm25_kernels_lean8.cu)
 
 }  // namespace prk

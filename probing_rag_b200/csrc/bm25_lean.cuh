@@ -1,31 +1,33 @@
-// Lean-step BM25 scoring kernel (tuning.mode 8, the default): the flat-step design of bm25_flat.cuh -- one warp
-// owns a (query, document-range) work item and a private 2048-document fp32 score tile in shared memory, applies
-// the query's terms in query-token order (one rounded fp32 add per posting: bit-identical to the reference's dense
-// accumulator) and runs ONE loop over step descriptors with the loads issued kPipe steps ahead -- with the
-// per-step overhead cut by a third and the shared-memory traffic by a third.  ncu on the flat kernel
-// (profiles/r01/v4_flat_kernel_ncu_summary.txt) showed ~60 warp instructions per 128-slot step and ~50 per 32-slot
-// step, most of them control: three step kinds decoded by nested branches, BRA.DIV guards in front of every vote,
-// two descriptor lists with bounds checks, 64-bit address assembly for CSR steps, S2R rematerialisation, a per-step
-// candidate list.  Here (history and numbers in DESIGN.md 4.1):
+// Lean-step BM25 scoring kernel -- the kernel behind pr_bm25_topk.  One warp owns a (query, document-range) work
+// item and a private 2048-document fp32 score tile in shared memory, applies the query's terms in query-token order
+// (one rounded fp32 add per posting: bit-identical to the reference's dense accumulator, /root/reference/exp_rag.py:426
+// -> bm25s `np.add.at`) and runs ONE loop over step descriptors with the posting loads issued kPipe
+// steps ahead.  History and ncu numbers of the kernels it replaced (CTA-cooperative, segment-loop, flat-step) are in
+// DESIGN.md 4.1 and profiles/r01.
 //
-//   * ONE posting address space.  Next to the hot stream the index keeps a COLD stream: every CSR posting as an
-//     interleaved (pre-scaled tile byte offset, weight) pair, 8 bytes, at granule index = posting index; hot narrow
-//     units are interleaved pairs too.  A descriptor is (granule index u32, flags): address = base + 8 * (granule +
-//     lane [* 2]).  Two step shapes remain: WIDE (4 slots per lane, two 128-bit loads) and NARROW (two 32-bit loads
+//   * ONE posting address space.  Next to the hot stream (bm25_hot.cuh) the index keeps a COLD stream: every CSR
+//     posting as an interleaved (pre-scaled tile byte offset, weight) pair, 8 bytes, at granule index = posting index;
+//     hot narrow units are interleaved pairs too.  A descriptor is (granule index u32, flags): address = base + 8 *
+//     (granule + lane [* 2]).  Two step shapes: WIDE (4 slots per lane, two 128-bit loads) and NARROW (one 64-bit load
 //     for the lanes below `cnt`; the others add +0.0f to a dummy word).  No-op and END steps are narrow steps with
 //     cnt = 0, so there is no third kind, and every per-step branch tests one flag bit of a word all lanes hold.
-//   * The two descriptor lists become one 128-entry ring; each produced list ends with a flagged descriptor (no
-//     loop counter) and is followed by kPipe no-op descriptors, so the look-ahead never needs a bounds check.
-//   * Threshold-on-update without candidate lists: each lane tracks the largest accumulator value it wrote; one
-//     vote at the end of a sub-tile decides whether the tile has to be scanned at all.
+//   * One 128-entry descriptor ring per warp; each produced list ends with a flagged descriptor (no loop counter) and
+//     is followed by kPipe no-op descriptors, so the look-ahead never needs a bounds check.
+//   * Threshold-on-update without candidate lists: each lane tracks the largest accumulator value it wrote; one vote
+//     at the end of a sub-tile decides whether the tile has to be scanned at all.
+//   * LIVE THRESHOLDS.  theta[q] is the best known lower bound of query q's final k-th score.  A warp reads it at the
+//     start of an item and again in front of every tile scan, and RAISES it with an
+//     atomicMax whenever the k-th score of its own item list exceeds it -- k documents with at least that score
+//     exist, so the final k-th score cannot be lower.  Items of the same query running at the same time on other
+//     SMs (and, through pr_bm25_topk_range + an all-reduce(MAX), on other GPUs) therefore filter with each other's
+//     thresholds inside one launch; no warm-up launches are needed.  The test against theta is NON-strict (a document
+//     that ties with a bound found elsewhere may still win on doc id); the merge applies the exact total order.
 //   * Sign epochs: every other sub-tile accumulates negated sums on top of the previous sub-tile's, so the tile is
 //     re-zeroed half as often.
 //   * Posting loads carry an L2 evict_last policy; items are handed out chunk-major.
-//
-// Mode 7 (rank-safe term skipping) stays with the flat kernel.
 #pragma once
 
-#include "bm25_flat.cuh"
+#include "bm25_hot.cuh"
 
 #ifndef PR_LEAN_PIPE
 #define PR_LEAN_PIPE 2
@@ -48,14 +50,45 @@ namespace prl {
 
 using prw::kSub;
 using prw::kSubShift;
-using prw::WarpArgs;
-using prf::kScanLimit;
-using prf::kTileWords;
-using prf::lds_f32;
-using prf::lds_u2;
-using prf::ldg_stream_f4;
-using prf::ldg_stream_u4;
-using prf::sts_f32;
+using prw::ScoreArgs;
+
+constexpr int kScanLimit = 4;          // lane-local forward scan of a rare term before the warp search
+constexpr int kTileWords = kSub + 32;  // + the dummy word the idle lanes of a narrow step add +0.0f to
+
+__device__ __forceinline__ float lds_f32(uint32_t a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ uint2 lds_u2(uint32_t a)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 ldg_stream_u4(const void *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 ldg_stream_f4(const void *p)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+// theta[q] is raised by other warps (and other GPUs) while this kernel runs: read it from L2, never from a cached line
+__device__ __forceinline__ float ld_theta(const float *p)
+{
+    float v;
+    asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+// scores are > 0 and the "nothing known" value is -1.0f, so the bit patterns order like the floats for every raise
+__device__ __forceinline__ void raise_theta(float *p, float v) { atomicMax(reinterpret_cast<int *>(p), __float_as_int(v)); }
 
 constexpr int kRing = 128;    // step descriptors in the per-warp ring (two lists + the trailing no-ops)
 constexpr int kListCap = 60;  // longest list one producer call lays out
@@ -123,9 +156,10 @@ static __global__ void __launch_bounds__(256) cold_fill_kernel(const int32_t *__
 
 template <int NW, int E>
 __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8 ? PR_LEAN_CTAS : NW <= 12 ? 2 : 1))
-    bm25_lean_kernel(const WarpArgs a)
+    bm25_lean_kernel(const ScoreArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (*reinterpret_cast<const volatile int32_t *>(a.status) & 2) return;  // inconsistent query CSR (bm25_init_kernel): touch nothing
     int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     asm volatile("" : "+r"(lane));  // opaque: kept in a register instead of being rematerialised by S2R in the step loop
@@ -170,17 +204,18 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
         const int c = item_i / a.n_queries, q = item_i - c * a.n_queries;
         const int64_t qb = a.q_indptr[q];
         const int nq = (int)(a.q_indptr[q + 1] - qb);
-        const float theta_run = a.run_theta[q];
-        const bool update_mode = theta_run > 0.f;
+        float *const theta_q = a.theta + q;
+        float theta_pub = ld_theta(theta_q);  // what this warp knows to be published (-1: nothing yet)
         item.reset();
-        float thr = fmaxf(theta_run, PR_DENORM_MIN);  // warp-uniform filter for candidates
+        // warp-uniform candidate filter, NON-strict: max(known bound on the final k-th score, k-th score of this item's
+        // list).  Without any bound it is the smallest positive float: every touched sub-tile is scanned.
+        float thr = fmaxf(theta_pub, PR_DENORM_MIN);
         float iks = PR_SENT_SCORE;
         int ikd = PR_SENT_DOC;
         const int sub0 = (a.chunk0 + c) * G;
         const int sub1 = min(sub0 + G, a.n_sub);
         const bool single = nq <= 32;
         float mx = 0.f;  // per lane: largest accumulator value written for the sub-tile being drained
-        float thr_push = update_mode ? thr : 0.f  /* no threshold yet: every sub-tile is scanned */;
 
         // ---- per-lane description of one query term (lane j <-> term p0+j of the current pass)
         // class: 2 = hot (steps from the hot stream, boundaries hot_off[t_row][g]), 1 = tabulated
@@ -648,7 +683,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
             const int base_doc = (g_end << kSubShift) + a.doc_id_base;
             auto consider = [&](float bs, int off) {  // warp-uniform arguments, exact score
                 const int bd = base_doc + off;
-                if (bs >= thr && bs > theta_run && pr_beats(bs, bd, iks, ikd)) {
+                if (bs >= thr && pr_beats(bs, bd, iks, ikd)) {
                     item.insert(bs, bd, lane);
                     item.kth(K, iks, ikd);
                     thr = fmaxf(thr, iks);
@@ -659,7 +694,19 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
             // once a threshold exists
             const bool odd = (hd & kOddBit) != 0;
             const float peak = odd ? -mx : mx;
-            if (!__any_sync(PR_FULL_MASK, peak >= thr_push)) {
+            bool scan = __any_sync(PR_FULL_MASK, peak >= thr);
+            if (scan) {
+                // about to scan: first look at what other warps (or GPUs) published since this item started.  Read here,
+                // synchronously, and only in front of a scan (under 1% of the sub-tiles once bounds exist): a load kept
+                // in flight across the sub-tile would share a scoreboard with the posting loads of the step loop.
+                const float t = ld_theta(theta_q);
+                if (t > thr) {
+                    thr = t;
+                    scan = __any_sync(PR_FULL_MASK, peak >= thr);
+                }
+                theta_pub = fmaxf(theta_pub, t);
+            }
+            if (!scan) {
                 if (odd || !PR_LEAN_SIGN_EPOCH) {
 #pragma unroll
                     for (int vv = lane & 31; vv < kSub / 4; vv += 32) tile4[vv] = zero4;
@@ -695,7 +742,10 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                 hd &= ~kOddBit;
             }
             mx = 0.f;
-            thr_push = update_mode ? thr : 0.f  /* no threshold yet: every sub-tile is scanned */;
+            if (iks > theta_pub) {  // this item alone holds k documents scoring >= iks: tell everyone scoring this query
+                if (lane == 0) raise_theta(theta_q, iks);
+                theta_pub = iks;
+            }
             __syncwarp();
         };
         // ---- one round of the ring: kPipe steps, each followed by the load of the step kPipe ahead

@@ -23,6 +23,7 @@
 //   prober_gate_kernel + compaction kernels
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -157,7 +158,29 @@ __device__ __forceinline__ void split_bf16(float y, __nv_bfloat16 &hi, __nv_bflo
 // ------------------------------------------------------------------- LN_in + split (kernel 0)
 // one warp per (row, prober): 2048 floats = 16 float4 per lane, statistics in fp32 exactly as
 // torch.nn.LayerNorm (biased variance, eps inside the sqrt)
-__global__ void __launch_bounds__(256) prober_ln_split_kernel(const float *__restrict__ X, const float *__restrict__ gamma,
+// four consecutive features of the pooled hidden states, whatever dtype the LM produced them in
+// (/root/reference/exp_rag.py:385-387 feeds the prober the LM's own dtype), widened to fp32
+template <typename T>
+__device__ __forceinline__ float4 load_x4(const T *x, int i);
+template <>
+__device__ __forceinline__ float4 load_x4<float>(const float *x, int i) { return reinterpret_cast<const float4 *>(x)[i]; }
+template <>
+__device__ __forceinline__ float4 load_x4<__nv_bfloat16>(const __nv_bfloat16 *x, int i)
+{
+    const uint2 u = reinterpret_cast<const uint2 *>(x)[i];
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xffff0000u));
+}
+template <>
+__device__ __forceinline__ float4 load_x4<__half>(const __half *x, int i)
+{
+    const uint2 u = reinterpret_cast<const uint2 *>(x)[i];
+    const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2 *>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) prober_ln_split_kernel(const T *__restrict__ X, const float *__restrict__ gamma,
                                                               const float *__restrict__ beta, __nv_bfloat16 *__restrict__ a_hi,
                                                               __nv_bfloat16 *__restrict__ a_lo, int n_rows, int rows_pad,
                                                               int n_probers, int d_model)
@@ -166,14 +189,14 @@ __global__ void __launch_bounds__(256) prober_ln_split_kernel(const float *__res
     const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (wid >= (int64_t)n_rows * n_probers) return;
     const int row = (int)(wid / n_probers), p = (int)(wid % n_probers);
-    const float4 *x4 = reinterpret_cast<const float4 *>(X + ((size_t)row * n_probers + p) * d_model);
-    const int nv = d_model >> 7;  // float4 per lane (16 for d_model = 2048)
+    const T *xrow = X + ((size_t)row * n_probers + p) * d_model;
+    const int nv = d_model >> 7;  // 4-feature groups per lane (16 for d_model = 2048)
     float4 v[16];
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; ++i)
         if (i < nv) {
-            v[i] = x4[lane + 32 * i];
+            v[i] = load_x4<T>(xrow, lane + 32 * i);
             sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
         }
     for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(PR_FULL_MASK, sum, o);
@@ -417,7 +440,7 @@ prober_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 // ------------------------------------------------------------------------ gate + compaction
 // P = sum_{l >= ablation} softmax(logits_l), in prober order; retrieve unless P0 + theta < P1
 // (/root/reference/exp_rag.py:407-415)
-__global__ void prober_gate_kernel(const float *__restrict__ probs, int n_rows, int n_probers, float theta, int ablation,
+__global__ void prober_gate_kernel(const float *__restrict__ probs, int n_rows, int n_probers, double theta, int ablation,
                                    float *__restrict__ probsum, uint8_t *__restrict__ mask, int32_t *__restrict__ block_cnt)
 {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
@@ -430,7 +453,9 @@ __global__ void prober_gate_kernel(const float *__restrict__ probs, int n_rows, 
         }
         probsum[(size_t)row * 2] = p0;
         probsum[(size_t)row * 2 + 1] = p1;
-        ret = !(p0 + theta < p1);
+        // the reference compares Python floats: `P0.item() + threshold < P1.item()` (exp_rag.py:414) -- the f32 sums
+        // widened to double, the threshold a double (0.1 is not an f32)
+        ret = !((double)p0 + theta < (double)p1);
         mask[row] = (uint8_t)ret;
     }
     const int c = __syncthreads_count(ret);
@@ -535,7 +560,7 @@ extern "C" size_t pr_prober_workspace_bytes(int32_t n_probers, int32_t n_rows, i
     return prober_layout(n_probers, n_rows, d_model, hidden).total;
 }
 
-extern "C" int pr_prober_forward(const pr_prober_set_t *ps, int32_t n_rows, const float *X_dev, float theta,
+extern "C" int pr_prober_forward(const pr_prober_set_t *ps, int32_t n_rows, const void *X_dev, int32_t x_dtype, double theta,
                                  int32_t ablation, float *out_logits_dev, float *out_probsum_dev,
                                  uint8_t *out_retrieve_mask_dev, int32_t *out_compact_idx_dev,
                                  int32_t *out_n_retrieve_dev, void *workspace_dev, size_t workspace_bytes,
@@ -552,6 +577,14 @@ extern "C" int pr_prober_forward(const pr_prober_set_t *ps, int32_t n_rows, cons
         pr_set_error("pr_prober_forward: unsupported shape (n_probers=%d d_model=%d hidden=%d; hidden must be 512, "
                      "d_model a multiple of 128 up to 2048)", P, ps->d_model, ps->hidden);
         return PR_EUNSUPPORTED;
+    }
+    if (x_dtype < 0 || x_dtype > 2) {
+        pr_set_error("pr_prober_forward: x_dtype must be 0 (f32), 1 (bf16) or 2 (f16), got %d", x_dtype);
+        return PR_EINVAL;
+    }
+    if ((uintptr_t)X_dev & 15) {
+        pr_set_error("pr_prober_forward: X_dev must be 16-byte aligned");
+        return PR_EINVAL;
     }
     if (ablation < 0 || ablation > P) {
         pr_set_error("pr_prober_forward: ablation %d outside [0, %d]", ablation, P);
@@ -581,8 +614,16 @@ extern "C" int pr_prober_forward(const pr_prober_set_t *ps, int32_t n_rows, cons
     // kernel 0: LN_in + split
     {
         const int64_t warps = (int64_t)n_rows * P;
-        prober_ln_split_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(X_dev, ps->ln_in_w, ps->ln_in_b, a1_hi, a1_lo,
-                                                                            n_rows, l.rows_pad, P, ps->d_model);
+        const unsigned nb = (unsigned)((warps + 7) / 8);
+        if (x_dtype == 0)
+            prober_ln_split_kernel<float><<<nb, 256, 0, st>>>((const float *)X_dev, ps->ln_in_w, ps->ln_in_b, a1_hi, a1_lo, n_rows,
+                                                              l.rows_pad, P, ps->d_model);
+        else if (x_dtype == 1)
+            prober_ln_split_kernel<__nv_bfloat16><<<nb, 256, 0, st>>>((const __nv_bfloat16 *)X_dev, ps->ln_in_w, ps->ln_in_b, a1_hi,
+                                                                      a1_lo, n_rows, l.rows_pad, P, ps->d_model);
+        else
+            prober_ln_split_kernel<__half><<<nb, 256, 0, st>>>((const __half *)X_dev, ps->ln_in_w, ps->ln_in_b, a1_hi, a1_lo, n_rows,
+                                                               l.rows_pad, P, ps->d_model);
         PR_CUDA_CHECK(cudaGetLastError());
     }
     CUtensorMap m_a1h, m_a1l, m_w1h, m_w1l, m_a2h, m_a2l, m_w2h, m_w2l;
@@ -625,6 +666,7 @@ extern "C" int pr_prober_forward(const pr_prober_set_t *ps, int32_t n_rows, cons
     PR_CUDA_CHECK(cudaGetLastError());
     // gate + ordered compaction of the rows that retrieve
     const int nb = (n_rows + 255) / 256;
+    PR_CUDA_CHECK(cudaMemsetAsync(out_compact_idx_dev, 0xff, (size_t)n_rows * 4, st));  // entries past n_retrieve read -1
     prober_gate_kernel<<<nb, 256, 0, st>>>(probs, n_rows, P, theta, ablation, out_probsum_dev, out_retrieve_mask_dev, block_cnt);
     prober_scan_kernel<<<1, 32, 0, st>>>(block_cnt, nb, out_n_retrieve_dev);
     prober_compact_kernel<<<nb, 256, 0, st>>>(out_retrieve_mask_dev, n_rows, block_cnt, out_compact_idx_dev);

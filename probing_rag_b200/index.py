@@ -205,16 +205,11 @@ class BM25Index:
         return float(ms.value), int(n.value)
 
     def aux_info(self) -> dict:
-        rows, min_df = ctypes.c_int32(), ctypes.c_int64()
-        _lib.check(_lib.lib().pr_index_aux_info(self._handle, ctypes.byref(rows), ctypes.byref(min_df)))
-        n_hot, hot_df, hot_bytes = ctypes.c_int32(), ctypes.c_int64(), ctypes.c_int64()
-        _lib.check(_lib.lib().pr_index_hot_info(self._handle, ctypes.byref(n_hot), ctypes.byref(hot_df),
-                                                 ctypes.byref(hot_bytes)))
-        lean_ok, cold_bytes = ctypes.c_int32(), ctypes.c_int64()
-        _lib.check(_lib.lib().pr_index_lean_info(self._handle, ctypes.byref(lean_ok), ctypes.byref(cold_bytes)))
-        return {"tp_rows": int(rows.value), "tp_min_df": int(min_df.value), "aux_bytes": int(self._aux.numel()),
-                "hot_rows": int(n_hot.value), "hot_min_df": int(hot_df.value), "hot_stream_bytes": int(hot_bytes.value),
-                "lean_ok": bool(lean_ok.value), "cold_stream_bytes": int(cold_bytes.value)}
+        info = _lib.AuxInfo()
+        _lib.check(_lib.lib().pr_index_aux_info(self._handle, ctypes.byref(info)))
+        out = {k: int(getattr(info, k)) for k, _ in _lib.AuxInfo._fields_}
+        out["aux_bytes"] = int(self._aux.numel())
+        return out
 
     @property
     def last_launches(self) -> int:
@@ -238,55 +233,122 @@ class BM25Index:
             self._ws_buf = buf = torch.empty(nbytes + nbytes // 4, dtype=torch.uint8, device=self.device)
         return buf
 
-    def topk(self, q_indptr: torch.Tensor, q_terms: torch.Tensor, k: int, out=None, check_status=True):
-        """Device CSR query batch -> (scores f32[B,k], doc_ids i32[B,k]) on the device.
-        Enqueues on the current stream; with check_status the stream is synchronised and a
-        bad term id raises ValueError like bm25s does (App. A.5)."""
-        nq = q_indptr.numel() - 1
+    def _check_query_batch(self, q_indptr: torch.Tensor, q_terms: torch.Tensor, k: int, out):
+        """Everything the C ABI cannot see from raw pointers: dtype, device, layout, sizes.  (The CSR's
+        CONTENT -- monotone offsets inside q_terms, term ids in range -- is validated on the device.)"""
         if k > self.n_docs_global:
             raise ValueError(f"k of {k} is larger than the number of documents {self.n_docs_global}")
         if not (1 <= k <= _lib.PR_MAX_K):
             raise ValueError(f"k must be in [1, {_lib.PR_MAX_K}] (got {k})")
         if q_indptr.dtype != torch.int64 or q_terms.dtype != torch.int32:
             raise ValueError("q_indptr must be int64 and q_terms int32")
+        if q_indptr.dim() != 1 or q_terms.dim() != 1 or q_indptr.numel() < 1:
+            raise ValueError("q_indptr must be a 1-D array of n_queries+1 offsets and q_terms 1-D")
+        for name, t in (("q_indptr", q_indptr), ("q_terms", q_terms)):
+            if not t.is_cuda or t.device != self.device:
+                raise ValueError(f"{name} must live on the index's device {self.device} (got {t.device})")
+        nq = q_indptr.numel() - 1
         if out is None:
             out = (torch.empty((nq, k), dtype=torch.float32, device=self.device),
                    torch.empty((nq, k), dtype=torch.int32, device=self.device))
+        else:
+            for t, dt in zip(out, (torch.float32, torch.int32)):
+                if (t.dtype != dt or tuple(t.shape) != (nq, k) or not t.is_cuda or t.device != self.device
+                        or not t.is_contiguous()):
+                    raise ValueError(f"out must be contiguous (float32[{nq},{k}], int32[{nq},{k}]) tensors on {self.device}")
+        return q_indptr.contiguous(), q_terms.contiguous(), nq, out
+
+    def topk(self, q_indptr: torch.Tensor, q_terms: torch.Tensor, k: int, out=None, check_status=True,
+             exchange=None, exchange_rounds: int | None = None):
+        """Device CSR query batch -> (scores f32[B,k], doc_ids i32[B,k]) on the device.
+        Enqueues on the current stream; with check_status the stream is synchronised and a bad
+        term id / inconsistent CSR raises ValueError like bm25s does (App. A.5).
+
+        exchange: optional callable(theta f32[B]) run between the launches of the call (doc-range
+        shards: an all-reduce(MAX) of the per-query k-th-score bounds over the ranks).
+        Every rank must join the same number of exchanges: `exchange_rounds` (>= this shard's launches - 1)
+        is what the longest shard needs, see `ShardedBM25`."""
+        q_indptr, q_terms, nq, out = self._check_query_batch(q_indptr, q_terms, k, out)
+        if nq == 0:
+            return out
         ws = self._workspace(nq, k)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         L = _lib.lib()
+        args = (self._handle, nq, q_indptr.data_ptr(), q_terms.data_ptr() if q_terms.numel() else None, q_terms.numel(), k,
+                out[0].data_ptr(), out[1].data_ptr(), ws.data_ptr(), ws.numel())
         with torch.cuda.device(self.device):
-            _lib.check(L.pr_bm25_topk(self._handle, nq, q_indptr.data_ptr(), q_terms.data_ptr(), k,
-                                      out[0].data_ptr(), out[1].data_ptr(), ws.data_ptr(), ws.numel(), stream))
+            if exchange is None or nq == 0:
+                _lib.check(L.pr_bm25_topk(*args, stream))
+            else:
+                n_launch = int(L.pr_bm25_num_launches(self._handle, nq, k, -1))
+                off = int(L.pr_bm25_theta_offset(self._handle, nq, k))
+                theta = ws[off:off + 4 * nq].view(torch.float32)
+                rounds = n_launch - 1 if exchange_rounds is None else max(int(exchange_rounds), n_launch - 1)
+                done = 0
+                for li in range(n_launch):
+                    _lib.check(L.pr_bm25_topk_range(*args, li, li + 1, stream))
+                    if done < rounds:
+                        exchange(theta)
+                        done += 1
+                for _ in range(rounds - done):              # a short shard still joins the rounds the longest one needs
+                    exchange(theta)
             if check_status and nq:
                 _lib.check(L.pr_bm25_status(ws.data_ptr(), stream))
         return out
 
-    def topk_host(self, q_indptr: np.ndarray, q_terms: np.ndarray, k: int):
+    def num_launches(self, n_queries: int, k: int, n_docs: int | None = None) -> int:
+        """Scoring launches of a call of this shape (on a shard of n_docs documents with this index's tuning)."""
+        n = int(_lib.lib().pr_bm25_num_launches(self._handle, n_queries, k, -1 if n_docs is None else int(n_docs)))
+        if n < 0:
+            raise ValueError(f"k must be in [1, {_lib.PR_MAX_K}] (got {k})")
+        return n
+
+    def check_status(self, n_queries: int, k: int) -> None:
+        """Synchronise the current stream and raise what the last topk of this shape flagged on the device."""
+        _lib.check(_lib.lib().pr_bm25_status(self._workspace(n_queries, k).data_ptr(),
+                                              torch.cuda.current_stream(self.device).cuda_stream))
+
+    def topk_host(self, q_indptr: np.ndarray, q_terms: np.ndarray, k: int, exchange=None):
         """Host CSR query batch -> host (scores, doc_ids): pinned H2D copy of the queries,
-        scoring, pinned D2H copy of the ranked lists.  Returns (scores, ids, h2d_bytes, d2h_bytes)."""
-        nq = len(q_indptr) - 1
-        key = (nq, len(q_terms), k)
-        bufs = self._pinned.get(key)
-        if bufs is None:
-            if len(self._pinned) > 8:
-                self._pinned.clear()
-            bufs = (torch.empty(nq + 1, dtype=torch.int64).pin_memory(),
-                    torch.empty(max(len(q_terms), 1), dtype=torch.int32).pin_memory(),
-                    torch.empty((nq, k), dtype=torch.float32).pin_memory(),
-                    torch.empty((nq, k), dtype=torch.int32).pin_memory())
-            self._pinned[key] = bufs
-        h_qi, h_qt, h_s, h_d = bufs
-        h_qi.numpy()[:] = q_indptr
-        h_qt.numpy()[:len(q_terms)] = q_terms
-        d_qi = h_qi.to(self.device, non_blocking=True)
-        d_qt = h_qt.to(self.device, non_blocking=True)
-        s, d = self.topk(d_qi, d_qt[:len(q_terms)] if len(q_terms) else d_qt[:0], k, check_status=False)
+        scoring, pinned D2H copy of the ranked lists.  Returns (scores, ids, h2d_bytes, d2h_bytes);
+        the arrays are the caller's own (copied out of the pinned staging buffers)."""
+        d_qi, d_qt, n_terms = self._stage_queries(q_indptr, q_terms)
+        s, d = self.topk(d_qi, d_qt, k, check_status=False, exchange=exchange)
+        h_s, h_d = self._unstage_lists(s, d)
+        _lib.check(_lib.lib().pr_bm25_status(self._workspace(len(q_indptr) - 1, k).data_ptr(),
+                                              torch.cuda.current_stream(self.device).cuda_stream))
+        return h_s.numpy().copy(), h_d.numpy().copy(), (len(q_indptr)) * 8 + n_terms * 4, (len(q_indptr) - 1) * k * 8
+
+    def _stage_queries(self, q_indptr: np.ndarray, q_terms: np.ndarray):
+        """Host CSR -> device tensors through pinned staging buffers (grown on demand, reused)."""
+        q_indptr = np.asarray(q_indptr)
+        q_terms = np.asarray(q_terms)
+        if q_indptr.ndim != 1 or len(q_indptr) < 1 or q_terms.ndim != 1:
+            raise ValueError("q_indptr must be a 1-D array of n_queries+1 offsets and q_terms 1-D")
+        n_i, n_t = len(q_indptr), len(q_terms)
+        st = self._pinned
+        if st.get("qi") is None or st["qi"].numel() < n_i:
+            st["qi"] = torch.empty(max(n_i, 1024), dtype=torch.int64).pin_memory()
+        if st.get("qt") is None or st["qt"].numel() < max(n_t, 1):
+            st["qt"] = torch.empty(max(n_t, 4096), dtype=torch.int32).pin_memory()
+        st["qi"].numpy()[:n_i] = q_indptr
+        st["qt"].numpy()[:n_t] = q_terms
+        d_qi = st["qi"][:n_i].to(self.device, non_blocking=True)
+        d_qt = st["qt"][:n_t].to(self.device, non_blocking=True)
+        return d_qi, d_qt, n_t
+
+    def _unstage_lists(self, s: torch.Tensor, d: torch.Tensor):
+        """Device [B,k] lists -> pinned host tensors (views of the staging buffers; valid until the next call)."""
+        n = s.numel()
+        st = self._pinned
+        if st.get("s") is None or st["s"].numel() < max(n, 1):
+            st["s"] = torch.empty(max(n, 4096), dtype=torch.float32).pin_memory()
+            st["d"] = torch.empty(max(n, 4096), dtype=torch.int32).pin_memory()
+        h_s = st["s"][:n].view(s.shape)
+        h_d = st["d"][:n].view(d.shape)
         h_s.copy_(s, non_blocking=True)
         h_d.copy_(d, non_blocking=True)
-        _lib.check(_lib.lib().pr_bm25_status(self._workspace(nq, k).data_ptr(),
-                                              torch.cuda.current_stream(self.device).cuda_stream))
-        return h_s.numpy(), h_d.numpy(), h_qi.numel() * 8 + len(q_terms) * 4, nq * k * 8
+        return h_s, h_d
 
     def algorithmic_bytes(self, q_indptr, q_terms, k: int) -> int:
         """sum_q (8 * sum_{t in q} df_shard(t) + 8*k)."""

@@ -18,6 +18,8 @@ from torch import nn
 
 from . import _lib
 
+_X_DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}   # pr_prober_forward x_dtype codes
+
 STATE_KEYS = (
     "layer_norm_input.weight", "layer_norm_input.bias",
     "fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "fc3.weight", "fc3.bias",
@@ -75,7 +77,9 @@ class ImprovedProbe(nn.Module):
 class GateOutput:
     probsum: torch.Tensor          # f32[B, 2]   sum over probers >= ablation of softmax(logits)   (exp_rag.py:407-410)
     retrieve: torch.Tensor         # bool[B]     NOT (probsum[0] + theta < probsum[1])             (exp_rag.py:414-415)
-    retrieve_idx: torch.Tensor     # i32[n]      rows that retrieve, ascending (device; sliced after one sync)
+    retrieve_idx: torch.Tensor     # i32[n]      rows that retrieve, ascending (device).  sync=True: exactly the n valid
+                                   #             entries; sync=False: all B slots, the first n_retrieve valid, the rest -1
+    n_retrieve: torch.Tensor       # i32[1]      on the device (no host sync needed to use the async result)
     logits: torch.Tensor | None    # f32[B, P, 2]
 
 
@@ -131,10 +135,14 @@ class ProberGate:
     @torch.no_grad()
     def __call__(self, X: torch.Tensor, theta: float = 0.0, ablation: int = 0, want_logits: bool = False,
                  sync: bool = True) -> GateOutput:
-        """X f32[B, P, d_model] on the gate's device."""
+        """X [B, P, d_model] pooled hidden states: f32, bf16 or f16 (read as they are -- a bf16 LM's sums
+        need no widening pass), anything else is converted to f32."""
         if X.dim() != 3 or X.shape[1] != self.n_probers or X.shape[2] != self.d_model:
             raise ValueError(f"X must be [B, {self.n_probers}, {self.d_model}], got {tuple(X.shape)}")
-        X = X.to(self.device, torch.float32).contiguous()
+        x_dtype = _X_DTYPES.get(X.dtype)
+        if x_dtype is None:
+            X, x_dtype = X.to(torch.float32), 0
+        X = X.to(self.device).contiguous()
         n = X.shape[0]
         dev = self.device
         logits = torch.empty((n, self.n_probers, 2), dtype=torch.float32, device=dev) if want_logits else None
@@ -146,12 +154,12 @@ class ProberGate:
         ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().pr_prober_forward(
-                ctypes.byref(self._set), n, X.data_ptr(), float(theta), int(ablation),
+                ctypes.byref(self._set), n, X.data_ptr(), x_dtype, float(theta), int(ablation),
                 logits.data_ptr() if want_logits else None, probsum.data_ptr(), mask.data_ptr(), compact.data_ptr(),
                 n_ret.data_ptr(), ws_ptr, ws.numel() - (ws_ptr - ws.data_ptr()),
                 torch.cuda.current_stream(dev).cuda_stream))
         idx = compact[: int(n_ret.item())] if sync else compact
-        return GateOutput(probsum=probsum, retrieve=mask.bool(), retrieve_idx=idx, logits=logits)
+        return GateOutput(probsum=probsum, retrieve=mask.bool(), retrieve_idx=idx, n_retrieve=n_ret, logits=logits)
 
 
 def gate_and_retrieve(gate: ProberGate, retriever, X: torch.Tensor, q_indptr: torch.Tensor, q_terms: torch.Tensor,

@@ -7,11 +7,15 @@ GLOBAL constants N, avgdl, df.  One process per GPU (torchrun):
     rank g owns docs [g*ceil(N/G), (g+1)*ceil(N/G))                       shard_range
     df and the token count are summed over ranks once, at build time       global_stats
     every rank scores the whole query batch against its shard              BM25Index.topk
+      between the launches of that call the per-query lower bounds of the
+      final k-th score are raised to the best any rank knows               exchange_thresholds
     [B,k] (score, doc id) lists are all-gathered                           gather_lists
     and merged in the canonical order (score desc, doc id asc)             pr_topk_merge
 
 The merged lists equal the single-index lists bit for bit: each document is scored on exactly
-one rank with the same weights and the same fp32 summation order.  The collective plumbing
+one rank with the same weights and the same fp32 summation order, and a bound found on one
+rank (k documents there score at least that much) can never exclude a document of the global
+top-k on another (the global k-th score is >= every rank's local k-th score).  The collective plumbing
 below is backend-agnostic (NCCL on the GPUs, gloo in the CPU tests); the scoring and the merge
 are CUDA only (`local_topk` / `merge` are injectable so the host logic can be tested with the
 oracle standing in as the checker).
@@ -65,13 +69,23 @@ def gather_lists(scores: torch.Tensor, ids: torch.Tensor, group=None, out=None):
     return out
 
 
+def exchange_thresholds(theta: torch.Tensor, group=None) -> None:
+    """theta f32[B] (-1 = no bound yet) <- elementwise maximum over the ranks, in place.  262 KB at 64k
+    queries: a latency-sized all-reduce, enqueued behind the launch that produced the bounds."""
+    if _world(group) > 1:
+        dist.all_reduce(theta, op=dist.ReduceOp.MAX, group=group)
+
+
 class ShardedBM25:
-    """This rank's shard + the exchange step.  `local_topk(q_indptr, q_terms, k) -> (scores, ids)`
-    defaults to the shard's CUDA kernel, `merge([G,B,k], [G,B,k]) -> ([B,k], [B,k])` to
-    pr_topk_merge."""
+    """This rank's shard + the exchange steps.  `local_topk(q_indptr, q_terms, k) -> (scores, ids)`
+    defaults to the shard's CUDA kernel (with the threshold exchange between its launches),
+    `merge([G,B,k], [G,B,k]) -> ([B,k], [B,k])` to pr_topk_merge.  Every rank returns the same
+    global lists, so a `BM25Retriever(index=ShardedBM25(shard))` behaves like the single-index one."""
+
+    doc_id_base = 0          # the merged lists carry global doc ids
 
     def __init__(self, index=None, group=None, local_topk: Callable | None = None,
-                 merge: Callable | None = None):
+                 merge: Callable | None = None, exchange: bool = True):
         if index is None and local_topk is None:
             raise ValueError("pass the shard's BM25Index or a local_topk callable")
         self.index = index
@@ -79,16 +93,49 @@ class ShardedBM25:
         self._local = local_topk
         self._merge = merge
         self._gath = {}
+        self._exchange = bool(exchange) and index is not None and local_topk is None and _world(group) > 1
+        self._max_docs = None
+        if self._exchange:
+            # every rank must join the same number of all-reduces per call: as many as the LONGEST shard has launches
+            n = torch.tensor([index.n_docs], dtype=torch.int64, device=index.device)
+            dist.all_reduce(n, op=dist.ReduceOp.MAX, group=group)
+            self._max_docs = int(n.item())
 
-    def topk(self, q_indptr, q_terms, k: int):
+    @property
+    def n_docs_global(self) -> int:
+        return self.index.n_docs_global if self.index is not None else -1
+
+    def _local_topk(self, q_indptr, q_terms, k: int):
         if self._local is not None:
-            s, d = self._local(q_indptr, q_terms, k)
-        else:
-            s, d = self.index.topk(q_indptr, q_terms, k, check_status=False)
+            return self._local(q_indptr, q_terms, k)
+        if not self._exchange:
+            return self.index.topk(q_indptr, q_terms, k, check_status=False)
+        rounds = self.index.num_launches(q_indptr.numel() - 1, k, n_docs=self._max_docs) - 1
+        return self.index.topk(q_indptr, q_terms, k, check_status=False,
+                               exchange=lambda theta: exchange_thresholds(theta, self.group), exchange_rounds=rounds)
+
+    def topk(self, q_indptr, q_terms, k: int, check_status: bool = True):
+        s, d = self._local_topk(q_indptr, q_terms, k)
         key = (tuple(s.shape), s.device)
         gs, gd = gather_lists(s, d, self.group, self._gath.get(key))
+        if len(self._gath) > 64:
+            self._gath.clear()
         self._gath[key] = (gs, gd)
         if self._merge is not None:
             return self._merge(gs, gd)
         from .index import merge_topk
-        return merge_topk(gs, gd)
+        out = merge_topk(gs, gd)
+        if check_status and self.index is not None and s.shape[0]:
+            self.index.check_status(s.shape[0], k)      # bad term ids raise on the sharded path too
+        return out
+
+    def topk_host(self, q_indptr, q_terms, k: int):
+        """Host CSR batch -> host (scores, ids, h2d_bytes, d2h_bytes): pinned H2D of the queries, local
+        scoring, all-gather and merge ON THE DEVICE, one pinned D2H of the merged lists."""
+        if self.index is None:
+            raise ValueError("topk_host needs the shard's BM25Index")
+        d_qi, d_qt, n_terms = self.index._stage_queries(q_indptr, q_terms)
+        s, d = self.topk(d_qi, d_qt, k, check_status=False)
+        h_s, h_d = self.index._unstage_lists(s, d)
+        self.index.check_status(len(q_indptr) - 1, k)   # synchronises the stream: the copies have landed
+        return h_s.numpy().copy(), h_d.numpy().copy(), len(q_indptr) * 8 + n_terms * 4, (len(q_indptr) - 1) * k * 8

@@ -18,32 +18,24 @@ pytestmark = pytest.mark.gpu
 
 SCORE_RTOL = 1e-5
 
+DEFAULTS = dict(subs_per_item=24, warps_per_cta=8, docs_per_launch=393216, min_items=32768, items_per_warp=1)
+
+# launch plans that exercise every path of the live-threshold protocol (bm25_lean.cuh): one launch with all
+# thresholds travelling between warps, one chunk per launch (thresholds only through the merge), everything between
 TUNINGS = [
-    dict(threads=512, tile_docs=24576, tiles_per_item=4, mode=2),
-    dict(threads=512, tile_docs=24576, tiles_per_item=4, mode=1),
-    dict(threads=256, tile_docs=8192, tiles_per_item=3, mode=2, min_items=64),
-    dict(threads=1024, tile_docs=40960, tiles_per_item=1, mode=2, cand_cap=32),
-    dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304),
-    dict(mode=3, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304),
-    dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, lazy_zero=2),
-    dict(mode=3, subs_per_item=7, warps_per_cta=9, docs_per_launch=98304, lazy_zero=2),
-    dict(mode=4, subs_per_item=1, warps_per_cta=4, docs_per_launch=2048, min_items=1),      # one sub-tile per item, many launches
-    dict(mode=4, subs_per_item=5, warps_per_cta=16, docs_per_launch=1000000, min_items=100000),  # one launch
-    dict(mode=6, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304),                  # flat-step kernel
-    dict(mode=5, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304),
-    dict(mode=6, subs_per_item=1, warps_per_cta=4, docs_per_launch=2048, min_items=1),
-    dict(mode=6, subs_per_item=5, warps_per_cta=12, docs_per_launch=1000000, min_items=100000),
-    dict(mode=8, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304),                  # lean-step kernel (default)
-    dict(mode=8, subs_per_item=1, warps_per_cta=4, docs_per_launch=2048, min_items=1),
-    dict(mode=8, subs_per_item=5, warps_per_cta=12, docs_per_launch=1000000, min_items=100000),
-    dict(mode=8, subs_per_item=3, warps_per_cta=10, docs_per_launch=20000, min_items=2048),
-    dict(mode=7, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304),                  # + rank-safe term skipping
-    dict(mode=7, subs_per_item=4, warps_per_cta=8, docs_per_launch=8192),                    # many launches: skipping from launch 2 on
-    dict(mode=7, subs_per_item=1, warps_per_cta=4, docs_per_launch=2048, min_items=1),
-    dict(mode=7, subs_per_item=3, warps_per_cta=12, docs_per_launch=20000, min_items=2048),
-    dict(threads=512, tile_docs=2048, tiles_per_item=1, mode=2, min_items=1),   # many launches
-    dict(threads=512, tile_docs=16384, tiles_per_item=2, mode=1, min_items=100000),  # one launch
+    dict(),                                                                               # the default plan
+    dict(subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
+    dict(subs_per_item=1, warps_per_cta=4, docs_per_launch=2048, min_items=1, items_per_warp=1),   # one sub-tile per item and launch: 49 launches
+    dict(subs_per_item=5, warps_per_cta=12, docs_per_launch=1000000, min_items=100000),  # one launch
+    dict(subs_per_item=3, warps_per_cta=10, docs_per_launch=20000, min_items=2048),
+    dict(subs_per_item=24, warps_per_cta=8, items_per_warp=64),                           # items cut down to one sub-tile, one launch
+    dict(subs_per_item=2, warps_per_cta=8, docs_per_launch=8192, min_items=1, items_per_warp=1),
+    dict(subs_per_item=24, warps_per_cta=8, docs_per_launch=49152, min_items=1, items_per_warp=1),  # long items, 3 launches
 ]
+
+
+def tune(gi, **kw):
+    gi.set_tuning(**dict(DEFAULTS, **kw))
 
 
 def gpu_index(idx, **kw):
@@ -51,10 +43,14 @@ def gpu_index(idx, **kw):
     return BM25Index.from_arrays(idx["data"], idx["indices"], idx["indptr"], idx["num_docs"], **kw)
 
 
-def run_gpu(gi, q_indptr, q_terms, k):
+def to_dev(gi, q_indptr, q_terms):
     dev = gi.device
-    s, d = gi.topk(torch.from_numpy(np.ascontiguousarray(q_indptr, dtype=np.int64)).to(dev),
-                   torch.from_numpy(np.ascontiguousarray(q_terms, dtype=np.int32)).to(dev), k)
+    return (torch.from_numpy(np.ascontiguousarray(q_indptr, dtype=np.int64)).to(dev),
+            torch.from_numpy(np.ascontiguousarray(q_terms, dtype=np.int32)).to(dev))
+
+
+def run_gpu(gi, q_indptr, q_terms, k, **kw):
+    s, d = gi.topk(*to_dev(gi, q_indptr, q_terms), k, **kw)
     torch.cuda.synchronize()
     return s.cpu().numpy(), d.cpu().numpy()
 
@@ -74,17 +70,16 @@ def test_golden_fixture_on_gpu(golden_dir):
     g = np.load(os.path.join(golden_dir, "bm25_golden.npz"))
     idx = {"data": g["data"], "indices": g["indices"], "indptr": g["indptr"], "num_docs": len(g["doc_lens"])}
     gi = gpu_index(idx)
-    for tun in (dict(threads=256, tile_docs=1024, tiles_per_item=1, mode=2, min_items=1),
-                dict(threads=512, tile_docs=2048, tiles_per_item=2, mode=1)):
-        gi.set_tuning(**tun)
+    for tun in (dict(), dict(subs_per_item=1, warps_per_cta=4, docs_per_launch=2048, min_items=1, items_per_warp=1)):
+        tune(gi, **tun)
         s, d = run_gpu(gi, g["q_indptr"], g["q_terms"], int(g["k"]))
         assert_parity(s, d, g["scores"], g["ids"])
 
 
-@pytest.mark.parametrize("tun", TUNINGS, ids=lambda t: "-".join(f"{k[:4]}{v}" for k, v in t.items()))
+@pytest.mark.parametrize("tun", TUNINGS, ids=lambda t: "-".join(f"{k[:4]}{v}" for k, v in t.items()) or "default")
 def test_config1_100k_docs_1k_queries(small_corpus, corpus_gpu, tun):
-    """BASELINE config 1: 100k passages, 1,000 queries, top-10, every tuning variant."""
-    corpus_gpu.set_tuning(**dict(dict(lazy_zero=1), **tun))
+    """BASELINE config 1: 100k passages, 1,000 queries, top-10, every launch plan."""
+    tune(corpus_gpu, **tun)
     qi, qt = small_corpus["q_indptr"], small_corpus["q_terms"]
     os_, od = co.retrieve_batch(small_corpus["index"], qi, qt, 10, n_threads=8)
     gs, gd = run_gpu(corpus_gpu, qi, qt, 10)
@@ -95,45 +90,52 @@ def test_config1_100k_docs_1k_queries(small_corpus, corpus_gpu, tun):
 def test_depth_sweep(small_corpus, corpus_gpu, k):
     qi, qt = small_corpus["q_indptr"][:65], small_corpus["q_terms"]
     os_, od = co.retrieve_batch(small_corpus["index"], qi, qt, k, n_threads=8)
-    for tun in (dict(threads=512, tile_docs=24576, tiles_per_item=4, mode=2, min_items=2048, cand_cap=1024),
-                dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
-                dict(mode=3, subs_per_item=3, warps_per_cta=8, docs_per_launch=20000, min_items=2048),
-                dict(mode=6, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
-                dict(mode=5, subs_per_item=3, warps_per_cta=12, docs_per_launch=20000, min_items=2048),
-                dict(mode=8, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
-                dict(mode=8, subs_per_item=3, warps_per_cta=12, docs_per_launch=20000, min_items=2048),
-                dict(mode=7, subs_per_item=3, warps_per_cta=8, docs_per_launch=10000, min_items=2048)):
-        corpus_gpu.set_tuning(**tun)
+    for tun in (TUNINGS[0], TUNINGS[1], TUNINGS[2], TUNINGS[4], TUNINGS[5]):
+        tune(corpus_gpu, **tun)
         gs, gd = run_gpu(corpus_gpu, qi, qt, k)
         assert_parity(gs, gd, os_, od)
 
 
 @pytest.mark.parametrize("nq", [1, 2, 37])
 def test_small_batches(small_corpus, corpus_gpu, nq):
-    """The reference's own shape: one query at a time (exp_rag.py:426)."""
+    """The reference's own shape: one query at a time (exp_rag.py:426).  A single query leaves one list per
+    (sub-tile, query) item: the 32-warp merge takes over from 128 lists per query."""
     qi, qt = small_corpus["q_indptr"][:nq + 1], small_corpus["q_terms"]
     os_, od = co.retrieve_batch(small_corpus["index"], qi, qt, 10)
-    for tun in (dict(threads=512, tile_docs=24576, tiles_per_item=4, mode=2, min_items=2048, cand_cap=1024),
-                dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
-                dict(mode=6, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
-                dict(mode=8, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
-                dict(mode=8, subs_per_item=2, warps_per_cta=8, docs_per_launch=8192, min_items=2048),
-                dict(mode=7, subs_per_item=2, warps_per_cta=8, docs_per_launch=8192, min_items=2048)):
-        corpus_gpu.set_tuning(**tun)
+    for tun in TUNINGS:
+        tune(corpus_gpu, **tun)
         gs, gd = run_gpu(corpus_gpu, qi, qt, 10)
         assert_parity(gs, gd, os_, od)
 
 
+def test_single_query_over_many_sub_tiles_uses_the_wide_merge():
+    """1 query x 400k documents = 196 one-sub-tile items in one launch (> 128 lists: bm25_merge_wide_kernel),
+    for k up to 128 and queries of 1..24 terms."""
+    n_docs, vocab = 400_000, 1 << 16
+    toks, lens = synth.corpus_np(n_docs, vocab)
+    idx = bo.build_index(toks, lens, vocab)
+    gi = gpu_index(idx)
+    assert gi.aux_info()["n_sub_tiles"] == 196
+    qi, qt = synth.queries_np(24, vocab, idx["df"])
+    for k in (1, 10, 100, 128):
+        os_, od = co.retrieve_batch(idx, qi, qt, k, n_threads=8)
+        for b in (1, 3, 24):
+            sel = slice(0, b + 1)
+            gs, gd = run_gpu(gi, qi[sel], qt[:qi[b]], k)
+            assert gi.num_launches(b, k) == 1
+            assert_parity(gs, gd, os_[:b], od[:b])
+
+
 def test_long_transcript_queries(small_corpus, corpus_gpu):
     """Later-round queries are whole LM transcripts (exp_rag.py:428, 457): 64-1024 terms,
-    more than one planning pass (256 terms) per tile."""
+    many 32-term passes per sub-tile, posting cursors in the warp's scratch."""
     idx = small_corpus["index"]
     qi, qt = synth.queries_np(48, small_corpus["vocab"], idx["df"], kind="later")
     assert np.diff(qi).max() > 256
     os_, od = co.retrieve_batch(idx, qi, qt, 10, n_threads=8)
-    for mode in (1, 2, 3, 4, 5, 6, 7, 8):
-        corpus_gpu.set_tuning(threads=512, tile_docs=24576, tiles_per_item=2, mode=mode, min_items=2048,
-                              subs_per_item=4, warps_per_cta=8, docs_per_launch=98304 if mode < 7 else 16384)
+    for tun in (dict(), dict(subs_per_item=4, docs_per_launch=98304, min_items=2048),
+                dict(subs_per_item=4, docs_per_launch=16384, min_items=1, items_per_warp=1)):
+        tune(corpus_gpu, **tun)
         gs, gd = run_gpu(corpus_gpu, qi, qt, 10)
         assert_parity(gs, gd, os_, od)
 
@@ -151,19 +153,27 @@ def test_edge_queries(small_corpus, corpus_gpu):
     qi[1:] = np.cumsum([len(q) for q in queries])
     qt = np.array([t for q in queries for t in q], dtype=np.int32)
     os_, od = bo.retrieve_batch(idx, qi, qt, 10)
-    for tun in TUNINGS[:3] + TUNINGS[4:18]:
-        corpus_gpu.set_tuning(**tun)
+    for tun in TUNINGS:
+        tune(corpus_gpu, **tun)
         gs, gd = run_gpu(corpus_gpu, qi, qt, 10)
         assert_parity(gs, gd, os_, od)
     assert od[0].tolist() == list(range(10)) and gs[0].tolist() == [0.0] * 10
+    # a batch of nothing but empty queries, and an empty batch
+    e_s, e_d = run_gpu(corpus_gpu, np.zeros(4, np.int64), np.zeros(0, np.int32), 10)
+    assert e_d.tolist() == [list(range(10))] * 3 and not e_s.any()
+    z_s, z_d = run_gpu(corpus_gpu, np.zeros(1, np.int64), np.zeros(0, np.int32), 10)
+    assert z_s.shape == (0, 10) and z_d.shape == (0, 10)
 
 
 def test_errors_match_bm25s(small_corpus, corpus_gpu):
+    tune(corpus_gpu)
     qi = np.array([0, 1], np.int64)
     with pytest.raises(ValueError):                       # bm25s: k > num_docs -> ValueError
         run_gpu(corpus_gpu, qi, np.array([3], np.int32), 129)
     with pytest.raises(ValueError):                       # bm25s: token id out of range -> ValueError
         run_gpu(corpus_gpu, qi, np.array([small_corpus["vocab"]], np.int32), 10)
+    with pytest.raises(ValueError):
+        run_gpu(corpus_gpu, qi, np.array([-1], np.int32), 10)
     tiny = bo.build_index_loop([np.array([0, 1]), np.array([1])], 2)
     gt = gpu_index(tiny)
     with pytest.raises(ValueError):
@@ -171,6 +181,57 @@ def test_errors_match_bm25s(small_corpus, corpus_gpu):
     s, d = run_gpu(gt, qi, np.array([1], np.int32), 2)
     os_, od = bo.retrieve_batch(tiny, qi, np.array([1], np.int32), 2)
     assert_parity(s, d, os_, od)
+
+
+def test_malformed_query_batches_raise_instead_of_reading_out_of_bounds(small_corpus, corpus_gpu):
+    """Raw pointers cross the C ABI: the wrapper checks device / dtype / layout, the library checks the CSR's
+    content on the device and then scores nothing (no illegal address, the context survives)."""
+    tune(corpus_gpu)
+    gi = corpus_gpu
+    qi, qt = small_corpus["q_indptr"][:9], small_corpus["q_terms"][:int(small_corpus["q_indptr"][8])]
+    d_qi, d_qt = to_dev(gi, qi, qt)
+    good = gi.topk(d_qi, d_qt, 10)
+    with pytest.raises(ValueError, match="device"):
+        gi.topk(d_qi.cpu(), d_qt, 10)
+    with pytest.raises(ValueError, match="device"):
+        gi.topk(d_qi, d_qt.cpu(), 10)
+    with pytest.raises(ValueError, match="int64"):
+        gi.topk(d_qi.int(), d_qt, 10)
+    with pytest.raises(ValueError, match="out must"):
+        gi.topk(d_qi, d_qt, 10, out=(torch.empty((8, 10), device=gi.device), torch.empty((8, 9), dtype=torch.int32, device=gi.device)))
+    with pytest.raises(ValueError, match="out must"):
+        gi.topk(d_qi, d_qt, 10, out=(torch.empty((8, 10)), torch.empty((8, 10), dtype=torch.int32)))
+    # a strided view is made contiguous, not mis-read
+    wide = torch.stack([d_qt, d_qt], dim=1)
+    s, d = gi.topk(d_qi, wide[:, 0], 10)
+    assert torch.equal(s, good[0]) and torch.equal(d, good[1])
+    # CSR content: q_terms shorter than q_indptr says, offsets not starting at 0, decreasing offsets
+    with pytest.raises(ValueError, match="CSR"):
+        gi.topk(d_qi, d_qt[:-3], 10)
+    with pytest.raises(ValueError, match="CSR"):
+        gi.topk(d_qi + 1, d_qt, 10)
+    bad = d_qi.clone()
+    bad[3], bad[4] = d_qi[4], d_qi[3] - 1
+    with pytest.raises(ValueError, match="CSR"):
+        gi.topk(bad, d_qt, 10)
+    torch.cuda.synchronize()
+    s, d = gi.topk(d_qi, d_qt, 10)                         # the context and the handle are intact
+    assert torch.equal(s, good[0]) and torch.equal(d, good[1])
+
+
+def test_topk_host_returns_arrays_the_caller_owns(small_corpus, corpus_gpu):
+    """Two calls of the same shape (two retrieval rounds) must not alias each other's results."""
+    tune(corpus_gpu)
+    qi, qt = small_corpus["q_indptr"], small_corpus["q_terms"]
+    a_s, a_d, h2d, d2h = corpus_gpu.topk_host(qi[:9], qt[:qi[8]], 10)
+    keep_s, keep_d = a_s.copy(), a_d.copy()
+    b_qi = qi[8:17] - qi[8]
+    b_s, b_d, _, _ = corpus_gpu.topk_host(b_qi, qt[qi[8]:qi[16]], 10)
+    assert np.array_equal(a_s, keep_s) and np.array_equal(a_d, keep_d)
+    assert not np.array_equal(a_d, b_d)
+    assert h2d == 9 * 8 + int(qi[8]) * 4 and d2h == 8 * 10 * 8
+    os_, od = co.retrieve_batch(small_corpus["index"], qi[:17], qt, 10)
+    assert_parity(np.concatenate([a_s, b_s]), np.concatenate([a_d, b_d]), os_, od)
 
 
 def test_invalid_index_rejected():
@@ -187,7 +248,9 @@ def test_invalid_index_rejected():
 
 
 def test_tie_heavy_corpus():
-    """Many identical documents -> large exact-score tie groups cut at the k boundary."""
+    """Many identical documents -> large exact-score tie groups cut at the k boundary.  The live thresholds are
+    NON-strict bounds (a document tying with a bound found by another warp can still win on doc id): this is
+    the corpus where a strict test would lose documents."""
     rng = np.random.default_rng(5)
     base = [rng.integers(0, 40, size=int(rng.integers(4, 12))).astype(np.int32) for _ in range(25)]
     docs = [base[int(rng.integers(0, 25))].copy() for _ in range(30000)]
@@ -200,36 +263,27 @@ def test_tie_heavy_corpus():
     gi = gpu_index(idx)
     for k in (1, 10, 100):
         os_, od = bo.retrieve_batch(idx, qi, qt, k)
-        for tun in (dict(threads=256, tile_docs=4096, tiles_per_item=2, mode=2, min_items=1),
-                    dict(threads=256, tile_docs=4096, tiles_per_item=2, mode=1, min_items=100000),
-                    dict(threads=512, tile_docs=24576, tiles_per_item=1, mode=2, cand_cap=32),
-                    dict(mode=4, subs_per_item=2, warps_per_cta=4, docs_per_launch=4096, min_items=1),
-                    dict(mode=3, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=100000),
-                    dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
-                    dict(mode=4, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048, lazy_zero=2),
-                    dict(mode=6, subs_per_item=2, warps_per_cta=4, docs_per_launch=4096, min_items=1),
-                    dict(mode=5, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=100000),
-                    dict(mode=6, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
-                    dict(mode=8, subs_per_item=2, warps_per_cta=4, docs_per_launch=4096, min_items=1),
-                    dict(mode=8, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
-                    dict(mode=7, subs_per_item=2, warps_per_cta=4, docs_per_launch=4096, min_items=1),
-                    dict(mode=7, subs_per_item=3, warps_per_cta=8, docs_per_launch=8192, min_items=2048)):
-            gi.set_tuning(**dict(dict(lazy_zero=1), **tun))
-            gs, gd = run_gpu(gi, qi, qt, k)
-            assert_parity(gs, gd, os_, od)
+        for tun in (dict(), dict(subs_per_item=2, warps_per_cta=4, docs_per_launch=4096, min_items=1, items_per_warp=1),
+                    dict(subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
+                    dict(subs_per_item=1, warps_per_cta=12, items_per_warp=64),
+                    dict(subs_per_item=3, warps_per_cta=8, docs_per_launch=8192, min_items=2048)):
+            tune(gi, **tun)
+            for _ in range(3):                      # the order in which warps publish bounds varies from run to run
+                gs, gd = run_gpu(gi, qi, qt, k)
+                assert_parity(gs, gd, os_, od)
 
 
-@pytest.mark.parametrize("mode", [4, 6, 8])
-def test_without_boundary_tables_every_term_takes_the_cursor_path(small_corpus, mode):
+def test_without_boundary_tables_every_term_takes_the_cursor_path(small_corpus):
     """aux budget 0 -> no term is tabulated: the head terms (thousands of postings per sub-tile,
     clustered far beyond the lane-local scan limit) go through the rare-term cursor + warp search."""
     gi = gpu_index(small_corpus["index"], aux_budget_bytes=0)
-    assert gi.aux_info()["tp_rows"] == 0
+    info = gi.aux_info()
+    assert info["table_rows"] == 0 and info["hot_rows"] == 0 and info["cold_stream_bytes"] == 8 * gi.nnz
     qi, qt = small_corpus["q_indptr"][:201], small_corpus["q_terms"]
     os_, od = co.retrieve_batch(small_corpus["index"], qi, qt, 10, n_threads=8)
-    for tun in (dict(mode=mode, subs_per_item=12, warps_per_cta=8, docs_per_launch=98304),
-                dict(mode=mode, subs_per_item=3, warps_per_cta=4, docs_per_launch=8192, min_items=1)):
-        gi.set_tuning(**tun)
+    for tun in (dict(subs_per_item=12, warps_per_cta=8, docs_per_launch=98304),
+                dict(subs_per_item=3, warps_per_cta=4, docs_per_launch=8192, min_items=1, items_per_warp=1)):
+        tune(gi, **tun)
         gs, gd = run_gpu(gi, qi, qt, 10)
         assert_parity(gs, gd, os_, od)
     lq, lt = synth.queries_np(8, small_corpus["vocab"], small_corpus["index"]["df"], kind="later")
@@ -238,28 +292,74 @@ def test_without_boundary_tables_every_term_takes_the_cursor_path(small_corpus, 
     assert_parity(gs, gd, os_, od)
 
 
-def test_doc_range_shards_and_merge_equal_single_index(small_corpus, corpus_gpu):
+def build_shards(small_corpus, g):
+    idx, toks, lens = small_corpus["index"], small_corpus["tokens"], small_corpus["doc_lens"]
+    off = np.concatenate([[0], np.cumsum(lens, dtype=np.int64)])
+    n_docs = len(lens)
+    per = -(-n_docs // g)
+    shards = []
+    for r in range(g):
+        lo, hi = r * per, min((r + 1) * per, n_docs)
+        sh = bo.build_index(toks[off[lo]:off[hi]], lens[lo:hi], small_corpus["vocab"], n_docs_global=n_docs,
+                            avgdl_global=idx["avgdl"], df_global=idx["df"], doc_id_base=lo)
+        shards.append(gpu_index(sh, n_docs_global=n_docs, doc_id_base=lo))
+    return shards
+
+
+def test_doc_range_shards_and_merge_equal_single_index(small_corpus):
     """SURVEY 8e on one GPU: G doc-range shards built with global statistics, local top-k each,
     pr_topk_merge -> bit-identical to the single index."""
     from probing_rag_b200 import merge_topk
-    idx, toks, lens = small_corpus["index"], small_corpus["tokens"], small_corpus["doc_lens"]
     qi, qt = small_corpus["q_indptr"][:301], small_corpus["q_terms"]
-    ref_s, ref_d = co.retrieve_batch(idx, qi, qt, 10, n_threads=8)
-    off = np.concatenate([[0], np.cumsum(lens, dtype=np.int64)])
-    n_docs = len(lens)
+    ref_s, ref_d = co.retrieve_batch(small_corpus["index"], qi, qt, 10, n_threads=8)
     for g in (2, 3, 8):
-        per = -(-n_docs // g)
         ss, dd = [], []
-        for r in range(g):
-            lo, hi = r * per, min((r + 1) * per, n_docs)
-            sh = bo.build_index(toks[off[lo]:off[hi]], lens[lo:hi], small_corpus["vocab"], n_docs_global=n_docs,
-                                avgdl_global=idx["avgdl"], df_global=idx["df"], doc_id_base=lo)
-            gi = gpu_index(sh, n_docs_global=n_docs, doc_id_base=lo)
-            gi.set_tuning(mode=(4 if g == 2 else 2 if g == 3 else 7), docs_per_launch=98304 if g != 8 else 4096)
-            dev = gi.device
-            s, d = gi.topk(torch.from_numpy(qi).to(dev), torch.from_numpy(qt).to(dev), 10)
+        for gi in build_shards(small_corpus, g):
+            tune(gi, **(TUNINGS[1] if g == 2 else TUNINGS[0] if g == 3 else dict(docs_per_launch=4096, min_items=1)))
+            s, d = gi.topk(*to_dev(gi, qi, qt), 10)
             ss.append(s); dd.append(d)
         ms, md = merge_topk(torch.stack(ss), torch.stack(dd))
+        torch.cuda.synchronize()
+        assert_parity(ms.cpu().numpy(), md.cpu().numpy(), ref_s, ref_d)
+
+
+@pytest.mark.parametrize("g", [2, 4])
+def test_threshold_exchange_between_shards_keeps_the_merged_lists_bit_identical(small_corpus, g):
+    """The multi-GPU protocol on one GPU: the shards run launch by launch in lock step and, between launches,
+    every shard's per-query bound is raised to the MAXIMUM over the shards (what the all-reduce(MAX) of
+    ShardedBM25 does over NCCL).  A shard may then hold fewer than k candidates of its own -- the merged lists
+    must still equal the single index bit for bit, ties included."""
+    from probing_rag_b200 import _lib, merge_topk
+    qi, qt = small_corpus["q_indptr"][:301], small_corpus["q_terms"]
+    ref_s, ref_d = co.retrieve_batch(small_corpus["index"], qi, qt, 10, n_threads=8)
+    shards = build_shards(small_corpus, g)
+    nq, k = len(qi) - 1, 10
+    L = _lib.lib()
+    for tun in (dict(subs_per_item=2, docs_per_launch=4096, min_items=1, items_per_warp=1), dict(docs_per_launch=16384, min_items=1, subs_per_item=4)):
+        outs, calls, thetas = [], [], []
+        for gi in shards:
+            tune(gi, **tun)
+            d_qi, d_qt = to_dev(gi, qi, qt)
+            out = (torch.empty((nq, k), dtype=torch.float32, device=gi.device), torch.empty((nq, k), dtype=torch.int32, device=gi.device))
+            ws = gi._workspace(nq, k)
+            off = int(L.pr_bm25_theta_offset(gi._handle, nq, k))
+            thetas.append(ws[off:off + 4 * nq].view(torch.float32))
+            calls.append((gi, (gi._handle, nq, d_qi.data_ptr(), d_qt.data_ptr(), d_qt.numel(), k, out[0].data_ptr(), out[1].data_ptr(),
+                               ws.data_ptr(), ws.numel()), (d_qi, d_qt)))
+            outs.append(out)
+        n_launch = {gi.num_launches(nq, k) for gi in shards}
+        assert len(n_launch) == 1 and min(n_launch) > 1      # equal shards -> the same plan on every "rank"
+        stream = torch.cuda.current_stream().cuda_stream
+        raised = 0
+        for li in range(min(n_launch)):
+            for gi, args, _ in calls:
+                _lib.check(L.pr_bm25_topk_range(*args, li, li + 1, stream))
+            best = torch.stack(thetas).max(dim=0).values
+            raised += int(sum((best > t).sum() for t in thetas))
+            for t in thetas:
+                t.copy_(best)
+        assert raised > 0                                    # the exchange really changed some shard's bound
+        ms, md = merge_topk(torch.stack([o[0] for o in outs]), torch.stack([o[1] for o in outs]))
         torch.cuda.synchronize()
         assert_parity(ms.cpu().numpy(), md.cpu().numpy(), ref_s, ref_d)
 
@@ -277,6 +377,7 @@ def test_gpu_index_builder_bit_exact(small_corpus):
 
 def test_save_load_roundtrip(tmp_path, small_corpus, corpus_gpu):
     from probing_rag_b200 import BM25Index
+    tune(corpus_gpu)
     corpus_gpu.save(str(tmp_path / "ix"))
     gi = BM25Index.load(str(tmp_path / "ix"))
     qi, qt = small_corpus["q_indptr"][:33], small_corpus["q_terms"]
@@ -298,11 +399,8 @@ def test_retriever_text_level_drop_in():
     bm25 = BM25Retriever.from_defaults(docstore=store, similarity_top_k=5)
     res = bm25.retrieve("What is the capital city of France? The tower of Paris")
     assert len(res) == 5 and all(res[i].score >= res[i + 1].score for i in range(4))
-    toks, lens = [], []
-    for t in texts:
-        ids = bm25.vocab.encode_corpus_doc(t)
-        toks += ids; lens.append(len(ids))
-    ora = bo.build_index(np.array(toks), np.array(lens), len(bm25.vocab))
+    toks, lens = bm25.vocab.encode_corpus(texts)
+    ora = bo.build_index(toks, lens, len(bm25.vocab))
     q = np.array(bm25.vocab.encode_query("What is the capital city of France? The tower of Paris"), np.int32)
     os_, od = bo.retrieve(ora, q, 5)
     assert [int(r.node.id_) for r in res] == od.tolist()
@@ -318,31 +416,34 @@ def test_retriever_text_level_drop_in():
 def test_full_size_21m_properties():
     """BASELINE config 2 shape (21,015,324 passages): the oracle cannot score 64k queries here,
     so check a 24-query sample against the C oracle on the same arrays, plus size-independent
-    properties on a larger batch: rank order, mode-1 == mode-2, batch-split invariance."""
+    properties on a larger batch: rank order, launch-plan invariance, batch-split invariance."""
     import bench
     gi, qi, qt = bench.build_workload(synth.N_DOCS_WIKI, 1 << 22, 2048, torch.device("cuda"))
-    dev = gi.device
-    d_qi, d_qt = torch.from_numpy(qi).to(dev), torch.from_numpy(qt).to(dev)
-    gi.set_tuning(mode=2)
+    d_qi, d_qt = to_dev(gi, qi, qt)
+    tune(gi)
     s2, d2 = gi.topk(d_qi, d_qt, 10)
-    for mode in (1, 3, 4, 6, 7, 8):
-        gi.set_tuning(mode=mode)
+    for tun in (dict(docs_per_launch=49152, min_items=1), dict(subs_per_item=6, warps_per_cta=12),
+                dict(docs_per_launch=4000000, warps_per_cta=4)):
+        tune(gi, **tun)
         s1, d1 = gi.topk(d_qi, d_qt, 10)
-        assert torch.equal(s1, s2) and torch.equal(d1, d2), mode
+        assert torch.equal(s1, s2) and torch.equal(d1, d2), tun
+    tune(gi)
     assert bool((s2[:, :-1] >= s2[:, 1:]).all())
     tie = s2[:, :-1] == s2[:, 1:]
     assert bool((d2[:, :-1][tie] < d2[:, 1:][tie]).all())
-    sa, da = gi.topk(d_qi[:2], d_qt, 10)                    # B=1 path: doc range split over CTAs
-    assert torch.equal(sa, s2[:1]) and torch.equal(da, d2[:1])
+    for b in (1, 8, 64):                                       # small batches: one launch, thousands of lists per query
+        sa, da = gi.topk(d_qi[:b + 1], d_qt[:int(qi[b])], 10)
+        assert gi.num_launches(b, 10) == 1
+        assert torch.equal(sa, s2[:b]) and torch.equal(da, d2[:b])
     host = {"data": gi.weights.cpu().numpy(), "indices": gi.doc_ids.cpu().numpy(),
             "indptr": gi.indptr.cpu().numpy(), "num_docs": gi.n_docs}
     os_, od = co.retrieve_batch(host, qi[:25], qt, 10, n_threads=min(24, os.cpu_count() or 1))
     assert_parity(s2[:24].cpu().numpy(), d2[:24].cpu().numpy(), os_, od)
 
 
-def test_weights_outside_lazy_range_use_plain_accumulators(small_corpus):
-    """Weights outside [2^-30, 2^10] cannot carry epoch tags (bm25_warp.cuh): the index must
-    fall back to densely re-zeroed accumulators and still match the oracle bit for bit."""
+def test_extreme_weights(small_corpus):
+    """Weights far outside the usual BM25 range (2^-40 .. 2^12 times a normal weight): the sign-epoch
+    accumulators must still match the oracle bit for bit."""
     idx = dict(small_corpus["index"])
     data = idx["data"].copy()
     data[::7] *= np.float32(2.0 ** -40)          # tiny weights
@@ -351,8 +452,8 @@ def test_weights_outside_lazy_range_use_plain_accumulators(small_corpus):
     gi = gpu_index(idx)
     qi, qt = small_corpus["q_indptr"][:129], small_corpus["q_terms"]
     os_, od = co.retrieve_batch(idx, qi, qt, 10, n_threads=8)
-    for mode in (4, 3, 2, 7, 8):
-        gi.set_tuning(mode=mode, docs_per_launch=98304 if mode != 7 else 16384)
+    for tun in (dict(), dict(docs_per_launch=16384, min_items=1)):
+        tune(gi, **tun)
         gs, gd = run_gpu(gi, qi, qt, 10)
         assert_parity(gs, gd, os_, od)
 
@@ -380,8 +481,8 @@ def test_random_shapes(seed):
     gi = gpu_index(idx)
     for k in (1, min(10, n_docs), min(100, n_docs)):
         os_, od = co.retrieve_batch(idx, qi, qt, k, n_threads=8)
-        for tun in (dict(mode=8), dict(mode=8, subs_per_item=1, warps_per_cta=4, docs_per_launch=2048, min_items=1),
-                    dict(mode=8, subs_per_item=2, warps_per_cta=12, docs_per_launch=4096, min_items=1), dict(mode=6)):
-            gi.set_tuning(**tun)
+        for tun in (dict(), dict(subs_per_item=1, warps_per_cta=4, docs_per_launch=2048, min_items=1, items_per_warp=1),
+                    dict(subs_per_item=2, warps_per_cta=12, docs_per_launch=4096, min_items=1, items_per_warp=1)):
+            tune(gi, **tun)
             gs, gd = run_gpu(gi, qi, qt, k)
             assert_parity(gs, gd, os_, od)

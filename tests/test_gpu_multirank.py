@@ -1,0 +1,77 @@
+"""The N > 1 path on real hardware: one process per GPU over NCCL (torchrun layout), doc-range shards with the
+threshold exchange between launches, all-gather + merge -- the merged lists must be bit-identical to the
+single-index lists AND to the CPU oracle.  Skipped on a box with one GPU (the gloo tests cover the host logic
+there, tests/test_gpu_bm25.py the exchange protocol itself)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+N_DOCS, VOCAB, NQ = 300_000, 1 << 18, 512
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import bench
+        from probing_rag_b200.sharding import ShardedBM25
+        dev = torch.device("cuda", rank)
+        gi, qi, qt = bench.build_workload(N_DOCS, VOCAB, NQ, dev, rank, world)
+        # many launches per call so the exchange really runs; every rank the same number
+        gi.set_tuning(subs_per_item=2, docs_per_launch=16384, min_items=1, items_per_warp=1)
+        d_qi, d_qt = torch.from_numpy(qi).to(dev), torch.from_numpy(qt).to(dev)
+        res = {}
+        for name, sb in (("exchange", ShardedBM25(gi)), ("plain", ShardedBM25(gi, exchange=False))):
+            for k in (10, 100):
+                s, d = sb.topk(d_qi, d_qt, k)
+                hs, hd, h2d, d2h = sb.topk_host(qi, qt, k)
+                torch.cuda.synchronize()
+                assert np.array_equal(hs, s.cpu().numpy()) and np.array_equal(hd, d.cpu().numpy())
+                assert d2h == NQ * k * 8
+                res[f"{name}_s{k}"], res[f"{name}_d{k}"] = hs, hd
+        res["launches"] = np.array([gi.num_launches(NQ, 10)])
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), **res)
+        with pytest.raises(ValueError):                 # bad term ids raise on the sharded path too
+            ShardedBM25(gi).topk(d_qi, torch.full_like(d_qt, VOCAB), 10)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("world", [2, 4])
+def test_nccl_doc_shards_equal_single_index_and_oracle(tmp_path, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs, this box has {torch.cuda.device_count()}")
+    import torch.multiprocessing as mp
+
+    import bench
+    from oracle import c_oracle as co
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    gi, qi, qt = bench.build_workload(N_DOCS, VOCAB, NQ, torch.device("cuda", 0))
+    host = {"data": gi.weights.cpu().numpy(), "indices": gi.doc_ids.cpu().numpy(), "indptr": gi.indptr.cpu().numpy(),
+            "num_docs": gi.n_docs}
+    d_qi, d_qt = torch.from_numpy(qi).cuda(), torch.from_numpy(qt).cuda()
+    for k in (10, 100):
+        s1, d1 = gi.topk(d_qi, d_qt, k)
+        os_, od = co.retrieve_batch(host, qi, qt, k, n_threads=min(16, os.cpu_count() or 1))
+        assert np.array_equal(d1.cpu().numpy(), od) and np.array_equal(s1.cpu().numpy(), os_)
+        for r in range(world):
+            got = np.load(tmp_path / f"r{r}.npz")
+            assert int(got["launches"][0]) > 2
+            for name in ("exchange", "plain"):
+                assert np.array_equal(got[f"{name}_d{k}"], od), f"rank {r} {name}: merged doc ids differ (k={k})"
+                assert np.array_equal(got[f"{name}_s{k}"], os_), f"rank {r} {name}: merged scores differ (k={k})"

@@ -77,6 +77,56 @@ def test_large_mean_and_scale_inputs(gate6):
     assert (torch.softmax(out.logits.cpu(), -1) - torch.softmax(ref, -1)).abs().max().item() < PROB_ATOL
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_half_precision_hidden_states_are_read_as_they_are(gate6, dtype):
+    """exp_rag.py:385-387 feeds the prober whatever dtype the LM produced: bf16 / f16 sums go through the C ABI
+    unconverted (x_dtype) and must match the reference evaluated on the same (widened) values."""
+    probers, gate = gate6
+    x = po.make_hidden_states(300, seed=21)
+    if dtype == torch.float16:
+        x = x * (1.0 / 16.0)                       # keep the largest sums inside f16 range
+    xh = x.to(dtype)
+    ref = po.prober_logits(probers, xh.float())
+    out = gate(xh.cuda(), want_logits=True)
+    assert (torch.softmax(out.logits.cpu(), -1) - torch.softmax(ref, -1)).abs().max().item() < PROB_ATOL
+    check_gate(out, ref, 0.0, 0)
+    wide = gate(xh.float().cuda(), want_logits=True)           # the same values through the f32 path: same kernel maths
+    assert torch.equal(wide.logits, out.logits) and torch.equal(wide.retrieve, out.retrieve)
+
+
+def test_gate_compares_in_double_like_the_reference(gate6):
+    """exp_rag.py:414 `P0.item() + threshold < P1.item()` is Python-float arithmetic.  With the gate's own f32
+    sums as inputs the decision must match that expression EXACTLY for thresholds that are not f32 numbers
+    (0.1) and for thresholds placed on a row's boundary, where an f32 comparison flips."""
+    _, gate = gate6
+    x = po.make_hidden_states(2000, seed=33).cuda()
+    base = gate(x)
+    p = base.probsum.cpu().double()
+    for theta in (0.1, -0.1, 0.3, 1e-9, -1e-9):
+        out = gate(x, theta=theta)
+        assert torch.equal(out.probsum, base.probsum)
+        want = ~(p[:, 0] + theta < p[:, 1])
+        assert torch.equal(out.retrieve.cpu(), want), theta
+    # thresholds exactly on / one double-ulp around the boundary of individual rows
+    for r in (3, 500, 1999):
+        edge = float(p[r, 1] - p[r, 0])                      # P0 + edge == P1 in double
+        for theta in (edge, np.nextafter(edge, -np.inf), np.nextafter(edge, np.inf)):
+            out = gate(x, theta=float(theta))
+            want = ~(p[:, 0] + float(theta) < p[:, 1])
+            assert torch.equal(out.retrieve.cpu(), want)
+
+
+def test_async_gate_output_is_usable_without_a_host_sync(gate6):
+    _, gate = gate6
+    x = po.make_hidden_states(777, seed=5).cuda()
+    a = gate(x, sync=True)
+    b = gate(x, sync=False)
+    n = int(b.n_retrieve.item())
+    assert n == a.retrieve_idx.numel() == int(a.retrieve.sum())
+    assert b.retrieve_idx.shape == (777,)
+    assert torch.equal(b.retrieve_idx[:n], a.retrieve_idx) and bool((b.retrieve_idx[n:] == -1).all())
+
+
 def test_other_shapes():
     from probing_rag_b200.prober import ProberGate
     for d_model, layers in ((256, (6,)), (1024, (6, 8, 10))):

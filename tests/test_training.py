@@ -68,3 +68,45 @@ def test_train_steps_follow_the_reference_loop(tmp_path):
     assert set(sd) == set(STATE_KEYS) and all(v.device.type == "cpu" for v in sd.values())
     fresh = po.OracleImprovedProbe(256, 2)
     fresh.load_state_dict(sd)                       # utils.py:302-326 path: load_state_dict(torch.load(path))
+
+
+@pytest.mark.gpu
+def test_train_and_eval_steps_on_the_gpu_follow_the_reference_loop(tmp_path):
+    """SURVEY 8f-4 on the device the hot path runs on: the training step (tokens_mean inputs as one masked
+    reduction, CE-on-softmax, AdamW + ExponentialLR per batch) with the gemma-2b prober shape on cuda:0 tracks
+    the literal restatement of train.py:199-220 run on the CPU, the eval step goes through the fused tcgen05
+    forward, and the checkpoint it writes is the file utils.load_prober reads (train.py:344-345, utils.py:316)."""
+    torch.manual_seed(16)
+    d = 2048
+    mine = ImprovedProbe(d, 2)
+    ref = po.OracleImprovedProbe(d, 2)
+    ref.load_state_dict(copy.deepcopy(mine.state_dict()))
+    mine.dropout.p = ref.dropout.p = 0.0
+    tr = ProberTrainer(prober=mine, lr=1e-4, device="cuda")
+    opt = torch.optim.AdamW(ref.parameters(), lr=1e-4)
+    sch = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.995)
+    ref.train()
+    for step in range(3):
+        acts, labels, pred_lens = batch(200 + step, B=16, T=24, d=d)
+        l_ref, lr_ref = po.train_step_reference(ref, opt, sch, acts, labels, pred_lens)
+        l_gpu, lr_gpu = tr.train_step(acts.cuda(), labels.cuda(), pred_lens)
+        assert abs(l_gpu - l_ref) < 5e-4 and lr_gpu == pytest.approx(lr_ref)
+    assert next(tr.prober.parameters()).is_cuda
+    for k in STATE_KEYS:                             # AdamW moves a weight by <= lr per step (see the CPU test)
+        assert torch.allclose(tr.prober.state_dict()[k].cpu(), ref.state_dict()[k], rtol=0, atol=3 * 1e-4 + 1e-6), k
+    # eval step: fused forward on the device vs the plain module on the same weights
+    acts, labels, pred_lens = batch(77, B=40, T=24, d=d)
+    acc, n, loss = tr.eval_step(acts.cuda(), labels.cuda(), pred_lens)
+    ref.load_state_dict({k: v.cpu() for k, v in tr.prober.state_dict().items()})
+    ref.eval()
+    with torch.no_grad():
+        x = po.tokens_mean_reference(acts, labels, pred_lens)
+        probs = torch.softmax(ref(x), -1)
+        loss_ref = float(torch.nn.functional.cross_entropy(probs, labels).item())
+    assert n == 40 and abs(loss - loss_ref) < 1e-3
+    margin = (probs[:, 0] - probs[:, 1]).abs()
+    assert abs(acc - float((probs.argmax(-1) == labels).double().mean())) <= float((margin < 2e-3).sum()) / 40 + 1e-9
+    name = checkpoint_name(1.0, "google/gemma-2b", "tokens_mean", 2, 16, "resid_post", 1, root=str(tmp_path))
+    tr.save(name)
+    sd = torch.load(name)
+    assert set(sd) == set(STATE_KEYS) and all(v.device.type == "cpu" for v in sd.values())

@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
-    ap.add_argument("--grid", default="small")
+    ap.add_argument("--grid", default="plan")
     ap.add_argument("--configs", default="", help="semicolon list of 'k=v,k=v' overriding --grid")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -35,19 +35,9 @@ def main():
     print(json.dumps({"aux": gi.aux_info()}), flush=True)
     if args.configs:
         cfgs = [{kv.split("=")[0]: int(kv.split("=")[1]) for kv in c.split(",")} for c in args.configs.split(";")]
-    elif args.grid == "warp":
-        cfgs = [dict(mode=m, subs_per_item=g, warps_per_cta=nw, docs_per_launch=dpl)
-                for m, g, nw, dpl in itertools.product([4, 3], [12, 6, 24], [8, 16, 4], [98304, 49152, 196608])
-                if not (m == 3 and (nw != 8 or dpl != 98304))]
-    elif args.grid == "small":
-        cfgs = [dict(threads=th, tile_docs=td, tiles_per_item=s, mode=m)
-                for (th, td), s, m in itertools.product(
-                    [(512, 24576), (512, 16384), (256, 8192), (256, 12288), (1024, 49152), (512, 49152)],
-                    [2, 4], [1, 2])]
     else:
-        cfgs = [dict(threads=th, tile_docs=td, tiles_per_item=s, mode=m)
-                for th, td, s, m in itertools.product([256, 512, 1024], [8192, 16384, 24576, 32768, 49152],
-                                                      [1, 2, 4, 8], [1, 2]) if td % (4 * th) == 0]
+        cfgs = [dict(subs_per_item=g, warps_per_cta=nw, docs_per_launch=dpl)
+                for g, nw, dpl in itertools.product([24, 12, 48], [8, 12], [393216, 196608, 786432, 1572864])]
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     ref = None
     with open(args.out, "a") as f:

@@ -293,7 +293,8 @@ def main():
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
-    ap.add_argument("--no-exchange", action="store_true", help="N > 1: no threshold exchange between launches (A/B)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "allreduce", "none"],
+                    help="N > 1: how the shards share score bounds (p2p = live over NVLink peer memory)")
     ap.add_argument("--tune", default="", help="comma list key=value for pr_bm25_tuning_t")
     args = ap.parse_args()
 
@@ -349,7 +350,25 @@ def main():
     gi, qi, qt = build_workload(args.n_docs, args.vocab, nq, device, rank, world)
     if args.tune:
         gi.set_tuning(**{kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.tune.split(",")})
-    sharded = ShardedBM25(gi, exchange=not args.no_exchange) if world > 1 else None
+    sharded, exchange_used = None, None
+    if world > 1:
+        exchange_used = None if args.exchange == "none" else args.exchange
+        if exchange_used == "p2p":
+            # peer memory needs CUDA IPC between the ranks' GPUs; if this box cannot provide it, say so and use the
+            # all-reduce form of the same exchange (every rank takes the same branch: the failure is collective)
+            ok = torch.ones(1, device=device)
+            try:
+                sharded = ShardedBM25(gi, exchange="p2p", max_queries=nq)
+            except Exception as ex:
+                log(f"[bench] rank {rank}: peer-memory thresholds unavailable ({ex!r})")
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() == 0:
+                if sharded is not None:
+                    sharded.close()
+                sharded, exchange_used = None, "allreduce"
+        if sharded is None:
+            sharded = ShardedBM25(gi, exchange=exchange_used)
     d_qi = torch.from_numpy(qi).to(device)
     d_qt = torch.from_numpy(qt).to(device)
     out = (torch.empty((nq, k), dtype=torch.float32, device=device),
@@ -421,6 +440,8 @@ def main():
         dist.all_reduce(t)                       # total algorithmic bytes / postings over the shards
     alg_total, nnz_total = float(t[0].item()), int(t[1].item())
 
+    if world > 1:
+        sharded.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -478,7 +499,7 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": make_config(args, world, nnz_total),
         "plan": {"tuning": gi.get_tuning(), "scoring_launches_per_step": n_score_launches, "nnz_shard0": gi.nnz,
-                 "threshold_exchange": bool(world > 1 and not args.no_exchange)},
+                 "threshold_exchange": exchange_used},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e / args.steps},

@@ -44,7 +44,7 @@ typedef void *pr_stream_t; /* cudaStream_t */
 typedef struct pr_bm25_tuning {
     int32_t subs_per_item;   /* consecutive 2048-document sub-tiles one warp scores for one query (default 24; halved
                                 automatically for batches too small to give every resident warp items_per_warp items) */
-    int32_t warps_per_cta;   /* 4, 8 (default), 10 or 12 */
+    int32_t warps_per_cta;   /* 4, 8 (default) or 12 */
     int32_t docs_per_launch; /* document range one launch covers for large batches (default 393216); bounds the
                                 per-item list storage in the workspace ([n_queries][chunks per launch][k] pairs) */
     int32_t min_items;       /* a launch covers at least this many (query, chunk) work items (default 32768), so a
@@ -105,10 +105,10 @@ size_t pr_bm25_workspace_bytes(const pr_index_t *index, int32_t n_queries, int32
  *   rounded add per posting, exactly as the reference's dense accumulator does.
  *   out_scores_dev float[n_queries*k], out_doc_ids_dev int32[n_queries*k] (GLOBAL doc ids).
  * Fewer than k positive scores: the tail is filled with this shard's lowest doc ids at
- * score 0.0.  Both arrays are validated ON THE DEVICE, nothing is read out of bounds: a q_indptr that
- * does not start at 0, decreases or points past n_q_terms makes the call score nothing and
- * pr_bm25_status() report PR_EINVAL; a term id outside [0, n_terms) is skipped and reported as
- * PR_ERANGE (bm25s raises ValueError there, App. A.5). */
+ * score 0.0.  Both arrays are validated ON THE DEVICE, nothing is read out of bounds: a query whose
+ * q_indptr slice is negative, decreasing or not inside [0, n_q_terms) (or a batch whose offsets do not
+ * start at 0) scores nothing and makes pr_bm25_status() report PR_EINVAL; a term id outside
+ * [0, n_terms) is skipped and reported as PR_ERANGE (bm25s raises ValueError there, App. A.5). */
 int pr_bm25_topk(pr_index_t *index, int32_t n_queries, const int64_t *q_indptr_dev,
                  const int32_t *q_terms_dev, int64_t n_q_terms, int32_t k, float *out_scores_dev,
                  int32_t *out_doc_ids_dev, void *workspace_dev, size_t workspace_bytes,
@@ -130,6 +130,26 @@ int pr_bm25_topk_range(pr_index_t *index, int32_t n_queries, const int64_t *q_in
                        const int32_t *q_terms_dev, int64_t n_q_terms, int32_t k, float *out_scores_dev,
                        int32_t *out_doc_ids_dev, void *workspace_dev, size_t workspace_bytes,
                        int32_t launch_begin, int32_t launch_end, pr_stream_t stream);
+
+/* Thresholds shared LIVE between the GPUs of a doc-sharded corpus (one process per GPU, NVLink / NVSwitch peer
+ * memory) -- the fused form of the exchange above: every rank keeps float theta[2][capacity] in memory its peers can
+ * address (pr_peer_alloc / pr_peer_open: CUDA IPC), and a scoring warp that raises a query's bound raises it in all
+ * copies with system-scope atomic maxima, so the other shards filter with it while they are still scoring -- no
+ * collective, no launch boundary.  The two halves alternate from call to call (all ranks must issue the same
+ * sequence of pr_bm25_topk calls, which the all-gather that ends each sharded call enforces anyway).
+ *   local_dev             this rank's array (2 * capacity floats, from pr_peer_alloc); NULL = private thresholds again
+ *   peer_bases_host       host array of n_peers (<= PR_MAX_PEERS) device pointers: the peers' arrays as opened here
+ *   peer_table_dev        2 * PR_MAX_PEERS * sizeof(void *) bytes of device memory on this GPU, owned by the caller,
+ *                         which the library fills (the kernels index it)
+ * With peers set, pr_bm25_theta_offset() no longer describes where the bounds live. */
+#define PR_MAX_PEERS 15
+typedef struct pr_ipc_handle { unsigned char bytes[64]; } pr_ipc_handle_t;
+int pr_peer_alloc(int device, size_t bytes, void **out_dev, pr_ipc_handle_t *out_handle);
+int pr_peer_open(int device, const pr_ipc_handle_t *handle, void **out_dev);
+int pr_peer_close(void *dev);
+int pr_peer_free(void *dev);
+int pr_index_set_peer_thetas(pr_index_t *index, float *local_dev, int64_t capacity, int32_t n_peers,
+                             float *const *peer_bases_host, void *peer_table_dev);
 
 /* Reads the status word pr_bm25_topk left in the workspace (synchronises `stream`). */
 int pr_bm25_status(const void *workspace_dev, pr_stream_t stream);

@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("PR_LIB_PATH") or os.path.join(PKG_DIR, "libprobingrag
 PR_OK, PR_EINVAL, PR_ECUDA, PR_ERANGE, PR_EWORKSPACE, PR_EUNSUPPORTED = 0, -1, -2, -3, -4, -5
 PR_MAX_K = 128
 PR_PROBER_MAX = 8
+PR_MAX_PEERS = 15
 
 c_i32, c_i64, c_f32, c_vp, c_sz = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
 
@@ -55,6 +56,11 @@ SIGNATURES = {
     "pr_bm25_theta_offset": (c_sz, [c_vp, c_i32, c_i32]),
     "pr_bm25_topk_range": (ctypes.c_int, [c_vp, c_i32, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_sz, c_i32, c_i32,
                                           c_vp]),
+    "pr_peer_alloc": (ctypes.c_int, [ctypes.c_int, c_sz, ctypes.POINTER(c_vp), ctypes.c_char_p]),
+    "pr_peer_open": (ctypes.c_int, [ctypes.c_int, ctypes.c_char_p, ctypes.POINTER(c_vp)]),
+    "pr_peer_close": (ctypes.c_int, [c_vp]),
+    "pr_peer_free": (ctypes.c_int, [c_vp]),
+    "pr_index_set_peer_thetas": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, ctypes.POINTER(c_vp), c_vp]),
     "pr_bm25_status": (ctypes.c_int, [c_vp, c_vp]),
     "pr_bm25_last_launches": (c_i64, [c_vp]),
     "pr_index_set_profiling": (ctypes.c_int, [c_vp, ctypes.c_int]),

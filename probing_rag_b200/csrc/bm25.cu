@@ -18,12 +18,6 @@
 
 namespace {
 
-// scores > 0 and the "nothing known" value is -1.0f: bit patterns order like the floats for every raise
-__device__ __forceinline__ void theta_raise(float *p, float v)
-{
-    if (v > 0.f) atomicMax(reinterpret_cast<int *>(p), __float_as_int(v));
-}
-
 // Canonical zero-score tail: fewer than K positive scores -> the lowest local doc ids not listed yet.
 __device__ __forceinline__ void fill_zero_tail(float *out_s, int32_t *out_d, int K, int nvalid, int doc_id_base, int n_docs)
 {
@@ -94,8 +88,8 @@ __device__ __forceinline__ void merge_lists(WarpTopK<E> &L, float &ks, int &kd, 
 template <int E>
 __global__ void __launch_bounds__(128) bm25_merge_kernel(
     const float *__restrict__ part_s, const int32_t *__restrict__ part_d, int C,
-    int64_t stride_q, int64_t stride_c, float *run_s, int32_t *run_d, float *theta, int B,
-    int K, int finalize, float *out_s, int32_t *out_d, int doc_id_base, int n_docs)
+    int64_t stride_q, int64_t stride_c, float *run_s, int32_t *run_d, float *theta, float *const *peer_theta, int n_peers,
+    int B, int K, int finalize, float *out_s, int32_t *out_d, int doc_id_base, int n_docs)
 {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -121,7 +115,7 @@ __global__ void __launch_bounds__(128) bm25_merge_kernel(
                 run_d[(size_t)q * K + i] = L.d[e];
             }
         }
-        if (lane == 0) theta_raise(theta + q, ks);
+        if (ks > 0.f) prw::raise_theta(theta, peer_theta, n_peers, q, ks, lane);
     }
     if (finalize) {
         int nvalid = 0;
@@ -149,8 +143,8 @@ constexpr int kWideWarps = 32;
 template <int E>
 __global__ void __launch_bounds__(kWideWarps * 32) bm25_merge_wide_kernel(
     const float *__restrict__ part_s, const int32_t *__restrict__ part_d, int C, int64_t stride_q, int64_t stride_c,
-    float *run_s, int32_t *run_d, float *theta, int K, int finalize, float *out_s, int32_t *out_d, int doc_id_base,
-    int n_docs)
+    float *run_s, int32_t *run_d, float *theta, float *const *peer_theta, int n_peers, int K, int finalize, float *out_s,
+    int32_t *out_d, int doc_id_base, int n_docs)
 {
     extern __shared__ __align__(16) unsigned char merge_smem[];
     float *sh_s = reinterpret_cast<float *>(merge_smem);                    // [kWideWarps][K]
@@ -189,7 +183,7 @@ __global__ void __launch_bounds__(kWideWarps * 32) bm25_merge_wide_kernel(
             run_d[(size_t)q * K + i] = L.d[e];
         }
     }
-    if (lane == 0) theta_raise(theta + q, ks);
+    if (ks > 0.f) prw::raise_theta(theta, peer_theta, n_peers, q, ks, lane);
     if (finalize) {
         int nvalid = 0;
 #pragma unroll
@@ -208,28 +202,24 @@ __global__ void __launch_bounds__(kWideWarps * 32) bm25_merge_wide_kernel(
     }
 }
 
-// Workspace initialisation + validation of the query CSR (status bit 2: q_indptr does not start at 0, is not
-// monotone, or points past q_terms -- the scoring kernel then touches nothing and pr_bm25_status reports PR_EINVAL).
+// Workspace initialisation.  (The query CSR is validated by the scoring warps, item by item: bm25_lean.cuh.)
 __global__ void bm25_init_kernel(float *run_s, int32_t *run_d, float *theta, int64_t n_run, int B, int32_t *counters,
-                                 int n_counters, int32_t *status, const int64_t *__restrict__ q_indptr, int64_t n_q_terms)
+                                 int n_counters, int32_t *status)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_run) {
         run_s[i] = PR_SENT_SCORE;
         run_d[i] = PR_SENT_DOC;
     }
-    if (i < B) theta[i] = PR_SENT_SCORE;
+    // (peer-shared thresholds are cleared by the host side, one call ahead: theta == nullptr here)
+    if (i < B && theta) theta[i] = PR_SENT_SCORE;
     if (i < n_counters) counters[i] = 0;
-    if (blockIdx.x == 0) {  // one block clears the status word and then validates: no other block touches it
-        if (threadIdx.x == 0) *status = 0;
-        __syncthreads();
-        bool bad = false;
-        for (int j = threadIdx.x; j < B; j += blockDim.x) {
-            const int64_t b = q_indptr[j], e = q_indptr[j + 1];
-            bad |= b < 0 || b > e || e > n_q_terms || (j == 0 && b != 0);
-        }
-        if (bad) atomicOr(status, 2);
-    }
+    if (i == 0) *status = 0;
+}
+
+__global__ void bm25_fill_kernel(float *p, int64_t n, float v)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
 // index validation (pr_index_create): indptr monotone and consistent, doc ids in range and
@@ -266,7 +256,7 @@ __global__ void bm25_validate_kernel(const int64_t *indptr, const int32_t *doc_i
 }  // namespace
 
 // ------------------------------------------------------------------------------------ host
-constexpr int kNwChoices = 4;  // warps per CTA: 4, 8, 10, 12
+constexpr int kNwChoices = 3;  // warps per CTA: 4, 8, 12
 constexpr int kEChoices = 3;   // E = 1, 2, 4
 
 struct pr_index {
@@ -299,7 +289,14 @@ struct pr_index {
     uint32_t hot_base_g;
     // per-kernel launch configuration, resolved once (cudaFuncSetAttribute + occupancy query are host latency that a
     // single-query call would pay every time): occupancy by (warps-per-CTA choice, E choice), 0 = not resolved yet
-    int occ[kNwChoices][kEChoices];
+    int occ[kNwChoices][kEChoices][2];
+    // thresholds shared with the other GPUs of a doc-sharded corpus (pr_index_set_peer_thetas): our array of
+    // 2 x peer_capacity floats (one half per call parity), the device table of the peers' arrays, the call counter
+    float *peer_local;
+    float *const *peer_table;
+    int32_t n_peers;
+    int64_t peer_capacity;
+    uint64_t peer_calls;
 };
 
 namespace {
@@ -307,6 +304,7 @@ namespace {
 struct Layout {
     int n_chunks, C, L;
     int G;  // sub-tiles per work item actually used: tuning.subs_per_item, halved for small batches
+    std::vector<int> launch_chunk0, launch_chunks;  // launch li covers chunks [chunk0, chunk0 + chunks)
     size_t off_status, off_counters, off_theta, off_run_s, off_run_d, off_part_s, off_part_d, off_cursors, total;
 };
 
@@ -335,7 +333,26 @@ Layout make_layout(const pr_index *ix, int32_t B, int32_t K, int32_t n_sub_tiles
     if (c < 1) c = 1;
     if (c > l.n_chunks) c = l.n_chunks > 0 ? l.n_chunks : 1;
     l.C = (int)c;
-    l.L = (l.n_chunks + l.C - 1) / l.C;
+    // Launch plan.  Thresholds travel between the warps of a launch, but only as the k-th scores of single items; the
+    // merge after a launch publishes the k-th score of everything scored so far, which is much stronger while few
+    // documents have been seen (a sub-tile is scanned when ANY of its 2048 documents reaches the bound).  So a large
+    // batch starts with a one-chunk launch and doubles -- c0, c0, 2 c0, 4 c0, ... up to C chunks: on a short shard
+    // (8 GPUs: 2.6M documents each) the first full-size launch would be 15% of the range.  Between launches is also
+    // where doc-range shards exchange their bounds (pr_bm25_topk_range).
+    {
+        int64_t c0 = B > 0 ? (4096 + (int64_t)B - 1) / B : l.C;
+        if (c0 < 1) c0 = 1;
+        if (c0 > l.C || l.C >= l.n_chunks) c0 = l.C;  // (a batch that fits ONE launch keeps it: no merges, no tails)
+        int pos = 0, cl = (int)c0;
+        while (pos < l.n_chunks) {
+            const int take = cl < l.n_chunks - pos ? cl : l.n_chunks - pos;
+            l.launch_chunk0.push_back(pos);
+            l.launch_chunks.push_back(take);
+            pos += take;
+            cl = pos < l.C ? pos : l.C;
+        }
+        l.L = (int)l.launch_chunk0.size();
+    }
     size_t o = 0;
     l.off_status = o;   o = align_up(o + 64, 256);
     l.off_counters = o; o = align_up(o + (size_t)(l.L + 1) * 4, 256);
@@ -355,33 +372,34 @@ using prk::score_fn_t;
 
 inline int e_of(int k) { return k <= 32 ? 1 : (k <= 64 ? 2 : 4); }
 inline int e_idx(int E) { return E == 1 ? 0 : E == 2 ? 1 : 2; }
-inline int nw_idx(int nw) { return nw == 4 ? 0 : nw == 8 ? 1 : nw == 10 ? 2 : 3; }
+inline int nw_idx(int nw) { return nw == 4 ? 0 : nw == 8 ? 1 : 2; }
 
 const int kMergeWideMinLists = 128;  // lists per query and launch from which the 32-warp merge pays
 
 template <int E>
 int launch_merge_e(bool wide, dim3 grid, cudaStream_t st, const float *ps, const int32_t *pd, int C,
-                   int64_t sq, int64_t sc, float *rs, int32_t *rd, float *th, int B, int K, int fin, float *os,
-                   int32_t *od, int base, int n_docs)
+                   int64_t sq, int64_t sc, float *rs, int32_t *rd, float *th, float *const *pt, int np, int B, int K, int fin,
+                   float *os, int32_t *od, int base, int n_docs)
 {
     if (wide) {
         const size_t smem = (size_t)kWideWarps * K * 8;  // <= 32 KB
-        bm25_merge_wide_kernel<E><<<B, kWideWarps * 32, smem, st>>>(ps, pd, C, sq, sc, rs, rd, th, K, fin, os, od, base, n_docs);
+        bm25_merge_wide_kernel<E><<<B, kWideWarps * 32, smem, st>>>(ps, pd, C, sq, sc, rs, rd, th, pt, np, K, fin, os, od, base, n_docs);
     } else {
-        bm25_merge_kernel<E><<<grid, 128, 0, st>>>(ps, pd, C, sq, sc, rs, rd, th, B, K, fin, os, od, base, n_docs);
+        bm25_merge_kernel<E><<<grid, 128, 0, st>>>(ps, pd, C, sq, sc, rs, rd, th, pt, np, B, K, fin, os, od, base, n_docs);
     }
     PR_CUDA_CHECK(cudaGetLastError());
     return PR_OK;
 }
 
-int launch_merge(pr_index *ix, int E, cudaStream_t st, const float *ps, const int32_t *pd, int C, int64_t sq, int64_t sc,
-                 float *rs, int32_t *rd, float *th, int B, int K, int fin, float *os, int32_t *od, int base, int n_docs)
+int launch_merge(int E, cudaStream_t st, const float *ps, const int32_t *pd, int C, int64_t sq, int64_t sc,
+                 float *rs, int32_t *rd, float *th, float *const *pt, int np, int B, int K, int fin, float *os, int32_t *od,
+                 int base, int n_docs)
 {
-    const bool wide = ix && rs && C >= kMergeWideMinLists;
+    const bool wide = rs && C >= kMergeWideMinLists;
     const dim3 grid((unsigned)((B + 3) / 4));
-    if (E == 1) return launch_merge_e<1>(wide, grid, st, ps, pd, C, sq, sc, rs, rd, th, B, K, fin, os, od, base, n_docs);
-    if (E == 2) return launch_merge_e<2>(wide, grid, st, ps, pd, C, sq, sc, rs, rd, th, B, K, fin, os, od, base, n_docs);
-    return launch_merge_e<4>(wide, grid, st, ps, pd, C, sq, sc, rs, rd, th, B, K, fin, os, od, base, n_docs);
+    if (E == 1) return launch_merge_e<1>(wide, grid, st, ps, pd, C, sq, sc, rs, rd, th, pt, np, B, K, fin, os, od, base, n_docs);
+    if (E == 2) return launch_merge_e<2>(wide, grid, st, ps, pd, C, sq, sc, rs, rd, th, pt, np, B, K, fin, os, od, base, n_docs);
+    return launch_merge_e<4>(wide, grid, st, ps, pd, C, sq, sc, rs, rd, th, pt, np, B, K, fin, os, od, base, n_docs);
 }
 
 void default_tuning(pr_bm25_tuning_t *t)
@@ -396,9 +414,9 @@ void default_tuning(pr_bm25_tuning_t *t)
 int check_tuning(const pr_bm25_tuning_t &t)
 {
     if (t.subs_per_item < 1 || t.docs_per_launch < 1 || t.min_items < 1 || t.items_per_warp < 1 ||
-        (t.warps_per_cta != 4 && t.warps_per_cta != 8 && t.warps_per_cta != 10 && t.warps_per_cta != 12)) {
+        (t.warps_per_cta != 4 && t.warps_per_cta != 8 && t.warps_per_cta != 12)) {
         pr_set_error("bad tuning (subs_per_item=%d docs_per_launch=%d min_items=%d items_per_warp=%d warps_per_cta=%d; "
-                     "warps_per_cta is 4, 8, 10 or 12)",
+                     "warps_per_cta is 4, 8 or 12)",
                      t.subs_per_item, t.docs_per_launch, t.min_items, t.items_per_warp, t.warps_per_cta);
         return PR_EINVAL;
     }
@@ -455,6 +473,11 @@ extern "C" int pr_index_create(pr_index_t **out, int device, int64_t n_docs_glob
     }
     pr_index *ix = new pr_index();
     memset(ix->occ, 0, sizeof(ix->occ));
+    ix->peer_local = nullptr;
+    ix->peer_table = nullptr;
+    ix->n_peers = 0;
+    ix->peer_capacity = 0;
+    ix->peer_calls = 0;
     ix->device = device;
     ix->n_docs_global = n_docs_global;
     ix->doc_id_base = doc_id_base;
@@ -631,6 +654,41 @@ extern "C" int pr_index_aux_info(const pr_index_t *index, pr_index_aux_info_t *i
     return PR_OK;
 }
 
+extern "C" int pr_index_set_peer_thetas(pr_index_t *index, float *local_dev, int64_t capacity, int32_t n_peers,
+                                        float *const *peer_bases_host, void *peer_table_dev)
+{
+    if (!index) {
+        pr_set_error("pr_index_set_peer_thetas: null index");
+        return PR_EINVAL;
+    }
+    if (!local_dev) {  // back to thresholds private to this GPU
+        index->peer_local = nullptr;
+        index->peer_table = nullptr;
+        index->n_peers = 0;
+        index->peer_capacity = 0;
+        return PR_OK;
+    }
+    if (capacity < 1 || n_peers < 0 || n_peers > PR_MAX_PEERS || (n_peers > 0 && (!peer_bases_host || !peer_table_dev))) {
+        pr_set_error("pr_index_set_peer_thetas: bad argument (capacity=%lld n_peers=%d, at most %d peers)", (long long)capacity,
+                     n_peers, PR_MAX_PEERS);
+        return PR_EINVAL;
+    }
+    float *tab[2 * PR_MAX_PEERS];
+    for (int par = 0; par < 2; ++par)
+        for (int p = 0; p < PR_MAX_PEERS; ++p)
+            tab[par * PR_MAX_PEERS + p] = p < n_peers ? peer_bases_host[p] + (size_t)par * capacity : nullptr;
+    if (n_peers > 0) PR_CUDA_CHECK(cudaMemcpy(peer_table_dev, tab, sizeof(tab), cudaMemcpyHostToDevice));
+    bm25_fill_kernel<<<64, 256>>>(local_dev, 2 * capacity, PR_SENT_SCORE);
+    PR_CUDA_CHECK(cudaGetLastError());
+    PR_CUDA_CHECK(cudaDeviceSynchronize());
+    index->peer_local = local_dev;
+    index->peer_table = (float *const *)peer_table_dev;
+    index->n_peers = n_peers;
+    index->peer_capacity = capacity;
+    index->peer_calls = 0;
+    return PR_OK;
+}
+
 extern "C" int pr_index_set_profiling(pr_index_t *index, int enable)
 {
     if (!index) {
@@ -756,6 +814,21 @@ extern "C" int pr_bm25_topk_range(pr_index_t *index, int32_t n_queries, const in
     const int E = e_of(k);
     int32_t *counters = (int32_t *)(ws + l.off_counters);
     float *theta = (float *)(ws + l.off_theta);
+    float *theta_next = nullptr;
+    float *const *peer_tab = nullptr;
+    if (index->peer_local) {
+        // thresholds shared with the peer GPUs live outside the workspace, one half of the array per call parity
+        if (n_queries > index->peer_capacity) {
+            pr_set_error("pr_bm25_topk: %d queries, the peer threshold arrays hold %lld", n_queries, (long long)index->peer_capacity);
+            return PR_EINVAL;
+        }
+        if (launch_begin == 0) index->peer_calls++;
+        const int parity = (int)(index->peer_calls & 1);
+        theta = index->peer_local + (size_t)parity * index->peer_capacity;
+        theta_next = index->peer_local + (size_t)(parity ^ 1) * index->peer_capacity;
+        peer_tab = index->peer_table + parity * PR_MAX_PEERS;
+    }
+    const int n_peers = index->peer_local ? index->n_peers : 0;
     float *run_s = (float *)(ws + l.off_run_s);
     int32_t *run_d = (int32_t *)(ws + l.off_run_d);
     float *part_s = (float *)(ws + l.off_part_s);
@@ -765,21 +838,25 @@ extern "C" int pr_bm25_topk_range(pr_index_t *index, int32_t n_queries, const in
         const int64_t n_run = (int64_t)n_queries * k;
         int64_t n_init = n_run > l.L + 1 ? n_run : l.L + 1;
         if (n_init < n_queries) n_init = n_queries;
-        bm25_init_kernel<<<(unsigned)((n_init + 255) / 256), 256, 0, st>>>(run_s, run_d, theta, n_run, n_queries, counters,
-                                                                           l.L + 1, status, q_indptr_dev, n_q_terms);
+        if (theta_next) bm25_fill_kernel<<<64, 256, 0, st>>>(theta_next, index->peer_capacity, PR_SENT_SCORE);
+        bm25_init_kernel<<<(unsigned)((n_init + 255) / 256), 256, 0, st>>>(run_s, run_d, theta_next ? nullptr : theta, n_run, n_queries,
+                                                                           counters, l.L + 1, status);
         PR_CUDA_CHECK(cudaGetLastError());
         index->last_launches += 1;
     }
 
     if (l.L == 0)  // shard without documents: only the (empty) finalisation
-        return launch_merge(index, E, st, part_s, part_d, 0, 0, 0, run_s, run_d, theta, n_queries, k, 1, out_scores_dev,
-                            out_doc_ids_dev, index->doc_id_base, index->n_docs);
+        return launch_merge(E, st, part_s, part_d, 0, 0, 0, run_s, run_d, theta, peer_tab, n_peers, n_queries, k, 1,
+                            out_scores_dev, out_doc_ids_dev, index->doc_id_base, index->n_docs);
 
     const int nw = t.warps_per_cta;
     const int threads = nw * 32;
     const size_t smem = prl::lean_smem_bytes(nw);
-    const score_fn_t fn = pick_lean_fn(nw, E);
-    int &occ = index->occ[nw_idx(nw)][e_idx(E)];
+    // items of one query run side by side when the batch is smaller than the resident warps: those warps re-read the
+    // query's bound in front of tile scans (REFRESH variant of the kernel)
+    const bool refresh = (int64_t)n_queries < 2 * (int64_t)index->num_sms * kNominalWarpsPerSm;
+    const score_fn_t fn = pick_lean_fn(nw, E, refresh);
+    int &occ = index->occ[nw_idx(nw)][e_idx(E)][refresh ? 1 : 0];
     if (occ == 0) {
         PR_CUDA_CHECK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PR_CUDA_CHECK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -805,6 +882,8 @@ extern "C" int pr_bm25_topk_range(pr_index_t *index, int32_t n_queries, const in
     w.q_indptr = q_indptr_dev;
     w.q_terms = q_terms_dev;
     w.theta = theta;
+    w.peer_theta = peer_tab;
+    w.n_peers = n_peers;
     w.part_s = part_s;
     w.part_d = part_d;
     w.status = status;
@@ -818,8 +897,7 @@ extern "C" int pr_bm25_topk_range(pr_index_t *index, int32_t n_queries, const in
     w.subs_per_item = l.G;
 
     for (int li = launch_begin; li < launch_end; ++li) {
-        const int chunk0 = li * l.C;
-        const int Cl = l.C < l.n_chunks - chunk0 ? l.C : l.n_chunks - chunk0;
+        const int chunk0 = l.launch_chunk0[li], Cl = l.launch_chunks[li];
         const int64_t items = (int64_t)n_queries * Cl;
         int64_t grid = (int64_t)occ * index->num_sms;
         const int64_t need = (items + nw - 1) / nw;
@@ -841,8 +919,9 @@ extern "C" int pr_bm25_topk_range(pr_index_t *index, int32_t n_queries, const in
             PR_CUDA_CHECK(cudaEventRecord(index->ev[index->ev_used + 1], st));
             index->ev_used += 2;
         }
-        const int rc = launch_merge(index, E, st, part_s, part_d, Cl, (int64_t)Cl * k, k, run_s, run_d, theta, n_queries, k,
-                                    li == l.L - 1, out_scores_dev, out_doc_ids_dev, index->doc_id_base, index->n_docs);
+        const int rc = launch_merge(E, st, part_s, part_d, Cl, (int64_t)Cl * k, k, run_s, run_d, theta, peer_tab, n_peers,
+                                    n_queries, k, li == l.L - 1, out_scores_dev, out_doc_ids_dev, index->doc_id_base,
+                                    index->n_docs);
         if (rc != PR_OK) return rc;
         index->last_launches += 2;
     }
@@ -892,6 +971,6 @@ extern "C" int pr_topk_merge(int32_t n_queries, int32_t k, int32_t n_lists, cons
     }
     if (n_queries == 0) return PR_OK;
     // lists are [n_lists, n_queries, k]: query stride k, list stride n_queries*k
-    return launch_merge(nullptr, e_of(k), (cudaStream_t)stream, scores_dev, ids_dev, n_lists, k, (int64_t)n_queries * k,
-                        nullptr, nullptr, nullptr, n_queries, k, 1, out_scores_dev, out_ids_dev, 0, -1);
+    return launch_merge(e_of(k), (cudaStream_t)stream, scores_dev, ids_dev, n_lists, k, (int64_t)n_queries * k, nullptr,
+                        nullptr, nullptr, nullptr, 0, n_queries, k, 1, out_scores_dev, out_ids_dev, 0, -1);
 }

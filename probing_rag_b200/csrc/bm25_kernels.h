@@ -1,5 +1,5 @@
 // Picker of the templated scoring kernel.  The instantiations live in their own translation units
-// (bm25_kernels_lean*.cu) so the library compiles in parallel.
+// (bm25_kernels_lean*.cu, one per CTA shape) so the library compiles in parallel.
 #pragma once
 
 #include "bm25_tables.cuh"
@@ -8,7 +8,10 @@ namespace prk {
 
 typedef void (*score_fn_t)(const prw::ScoreArgs);
 
-score_fn_t pick_lean_fn(int nw, int E);   // nw = warps per CTA (4, 8, 10, 12), E = ceil(k / 32) rounded up to 1, 2, 4
-score_fn_t pick_lean_fn_nw8(int E);       // (bm25_kernels_lean8.cu)
+// nw = warps per CTA (4, 8, 12), E = ceil(k / 32) rounded up to 1, 2, 4, refresh = small-batch variant (bm25_lean.cuh)
+score_fn_t pick_lean_fn(int nw, int E, bool refresh);
+score_fn_t pick_lean_fn_nw4(int E, bool refresh);
+score_fn_t pick_lean_fn_nw8(int E, bool refresh);
+score_fn_t pick_lean_fn_nw12(int E, bool refresh);
 
 }  // namespace prk

@@ -1,14 +1,17 @@
-// Instantiations of prl::bm25_lean_kernel for the default CTA shape (8 warps, 3 CTAs per SM).
+// Instantiations of prl::bm25_lean_kernel for CTAs of 8 warps (the default: 3 CTAs per SM).
 #include "bm25_lean.cuh"
 #include "bm25_kernels.h"
 
 namespace prk {
 
-score_fn_t pick_lean_fn_nw8(int E)
+template <bool R>
+static score_fn_t pick(int E)
 {
-    if (E == 1) return prl::bm25_lean_kernel<8, 1>;
-    if (E == 2) return prl::bm25_lean_kernel<8, 2>;
-    return prl::bm25_lean_kernel<8, 4>;
+    if (E == 1) return prl::bm25_lean_kernel<8, 1, R>;
+    if (E == 2) return prl::bm25_lean_kernel<8, 2, R>;
+    return prl::bm25_lean_kernel<8, 4, R>;
 }
+
+score_fn_t pick_lean_fn_nw8(int E, bool refresh) { return refresh ? pick<true>(E) : pick<false>(E); }
 
 }  // namespace prk

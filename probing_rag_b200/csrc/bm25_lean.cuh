@@ -53,7 +53,9 @@ using prw::kSubShift;
 using prw::ScoreArgs;
 
 constexpr int kScanLimit = 4;          // lane-local forward scan of a rare term before the warp search
-constexpr int kTileWords = kSub + 32;  // + the dummy word the idle lanes of a narrow step add +0.0f to
+// + 32 dummy words (one per bank: what the idle lanes of a narrow step and the pad slots of the hot stream add +0.0f
+// to) + 4 words of per-warp scratch (word kSub + 32: the bound known at the item's start, see the kernel)
+constexpr int kTileWords = kSub + 32 + 4;
 
 __device__ __forceinline__ float lds_f32(uint32_t a)
 {
@@ -80,15 +82,8 @@ __device__ __forceinline__ float4 ldg_stream_f4(const void *p)
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }
-// theta[q] is raised by other warps (and other GPUs) while this kernel runs: read it from L2, never from a cached line
-__device__ __forceinline__ float ld_theta(const float *p)
-{
-    float v;
-    asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-    return v;
-}
-// scores are > 0 and the "nothing known" value is -1.0f, so the bit patterns order like the floats for every raise
-__device__ __forceinline__ void raise_theta(float *p, float v) { atomicMax(reinterpret_cast<int *>(p), __float_as_int(v)); }
+using prw::ld_theta;
+using prw::raise_theta;
 
 constexpr int kRing = 128;    // step descriptors in the per-warp ring (two lists + the trailing no-ops)
 constexpr int kListCap = 60;  // longest list one producer call lays out
@@ -154,12 +149,14 @@ static __global__ void __launch_bounds__(256) cold_fill_kernel(const int32_t *__
         cold[p] = make_uint2((uint32_t)(doc_ids[p] & (kSub - 1)) * 4u, __float_as_uint(weights[p]));
 }
 
-template <int NW, int E>
+// REFRESH: re-read theta[q] in front of tile scans (batches smaller than the resident warps, see end_subtile).  A
+// template parameter, not a run-time flag: with the flag ptxas put a YIELD into the step loop (-2% queries/s;
+// tests/test_capi.py checks the built kernels for it).
+template <int NW, int E, bool REFRESH>
 __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8 ? PR_LEAN_CTAS : NW <= 12 ? 2 : 1))
     bm25_lean_kernel(const ScoreArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    if (*reinterpret_cast<const volatile int32_t *>(a.status) & 2) return;  // inconsistent query CSR (bm25_init_kernel): touch nothing
     int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     asm volatile("" : "+r"(lane));  // opaque: kept in a register instead of being rematerialised by S2R in the step loop
@@ -203,9 +200,20 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
         // (ncu: 52% L2 hit rate with query-major order -- the slice's ~90 MB footprint overflows one L2 partition)
         const int c = item_i / a.n_queries, q = item_i - c * a.n_queries;
         const int64_t qb = a.q_indptr[q];
-        const int nq = (int)(a.q_indptr[q + 1] - qb);
+        int nq = (int)min(a.q_indptr[q + 1] - qb, (int64_t)0x7fffffff);
+        // raw pointers crossed the C ABI: a query whose CSR slice is not inside q_terms (or a batch whose offsets do not
+        // start at 0) is flagged -- pr_bm25_status reports PR_EINVAL -- and scores nothing; nothing is read out of bounds
+        if (qb < 0 || nq < 0 || qb + nq > a.n_q_terms || (q == 0 && qb != 0)) {
+            if (lane == 0) atomicOr(a.status, 2);
+            nq = 0;
+        }
         float *const theta_q = a.theta + q;
         float theta_pub = ld_theta(theta_q);  // what this warp knows to be published (-1: nothing yet)
+        // Large batches publish once, at the item's end, and only if the item's k-th score beats what was known at its
+        // start -- kept in a spare word of the tile meanwhile: one more live register in the step loop cost 1.3%
+        // queries/s on the full batch and 3.4% on a 2.6M-document shard.
+        const uint32_t stash_sa = tile_sa + (uint32_t)(kSub + 32) * 4u;
+        if (!REFRESH) sts_f32(stash_sa, theta_pub);
         item.reset();
         // warp-uniform candidate filter, NON-strict: max(known bound on the final k-th score, k-th score of this item's
         // list).  Without any bound it is the smallest positive float: every touched sub-tile is scanned.
@@ -696,15 +704,20 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
             const float peak = odd ? -mx : mx;
             bool scan = __any_sync(PR_FULL_MASK, peak >= thr);
             if (scan) {
-                // about to scan: first look at what other warps (or GPUs) published since this item started.  Read here,
-                // synchronously, and only in front of a scan (under 1% of the sub-tiles once bounds exist): a load kept
-                // in flight across the sub-tile would share a scoreboard with the posting loads of the step loop.
-                const float t = ld_theta(theta_q);
+                // about to scan: first look at what other warps published since this item started -- only when items of
+                // one query run side by side (a batch smaller than the resident warps; otherwise the query's previous
+                // item finished long before this one started and the read at the item's start saw all there is).
+                // Read here, synchronously, in front of a scan: a load kept in flight across the sub-tile would share a
+                // scoreboard with the posting loads of the step loop (measured: -4% queries/s on the full batch), and
+                // an unconditional read costs an L2 round trip per scanned sub-tile while bounds are still weak
+                // (+5% on the early launches of a short shard).  The other variant reads the tile's dummy word (+-0: a
+                // no-op) so that both have the same shape -- without any read here ptxas puts a YIELD into the step loop.
+                const float t = REFRESH ? ld_theta(theta_q) : lds_f32(tile_sa + dummy_off);
                 if (t > thr) {
                     thr = t;
                     scan = __any_sync(PR_FULL_MASK, peak >= thr);
                 }
-                theta_pub = fmaxf(theta_pub, t);
+                if (REFRESH) theta_pub = fmaxf(theta_pub, t);
             }
             if (!scan) {
                 if (odd || !PR_LEAN_SIGN_EPOCH) {
@@ -742,8 +755,8 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                 hd &= ~kOddBit;
             }
             mx = 0.f;
-            if (iks > theta_pub) {  // this item alone holds k documents scoring >= iks: tell everyone scoring this query
-                if (lane == 0) raise_theta(theta_q, iks);
+            if (REFRESH && iks > theta_pub) {  // this item alone holds k documents scoring >= iks: tell everyone scoring this query
+                raise_theta(a.theta, a.peer_theta, a.n_peers, q, iks, lane);
                 theta_pub = iks;
             }
             __syncwarp();
@@ -791,6 +804,8 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
             for (int vv = lane & 31; vv < kSub / 4; vv += 32) tile4[vv] = zero4;
             __syncwarp();
         }
+
+        if (!REFRESH && iks > lds_f32(stash_sa)) raise_theta(a.theta, a.peer_theta, a.n_peers, q, iks, lane);
 
         float *ps = a.part_s + ((size_t)q * C + c) * K;
         int32_t *pdst = a.part_d + ((size_t)q * C + c) * K;

@@ -15,6 +15,27 @@
 
 namespace prw {
 
+// theta[q]: lower bound of query q's final k-th score, shared by everything that scores the query -- the warps of
+// this GPU and, for a doc-sharded corpus, the other GPUs of the box.  Scores are > 0 and "nothing known" is -1.0f, so
+// the bit patterns order like the floats for every raise.  Raising is an atomicMax on our copy plus one system-scope
+// atomicMax per peer copy, issued by lanes 1..n_peers over NVLink (fire-and-forget reductions; a bound is advisory
+// and monotone, so relaxed ordering is enough).  Reads are of our own copy only.
+__device__ __forceinline__ float ld_theta(const float *p)
+{
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void raise_theta(float *local, float *const *peer_theta, int n_peers, int q, float v, int lane)
+{
+    if (lane == 0) {
+        atomicMax(reinterpret_cast<int *>(local + q), __float_as_int(v));
+    } else if (lane <= n_peers) {
+        int *dst = reinterpret_cast<int *>(peer_theta[lane - 1] + q);
+        asm volatile("red.relaxed.sys.global.max.s32 [%0], %1;" ::"l"(dst), "r"(__float_as_int(v)) : "memory");
+    }
+}
+
 constexpr int kSubShift = PR_SUB_SHIFT;
 constexpr int kSub = 1 << kSubShift;  // documents per warp sub-tile (8 KB of fp32)
 constexpr int kLightDf = 128;         // smallest df threshold of the boundary table
@@ -34,6 +55,8 @@ struct ScoreArgs {
     const int32_t *__restrict__ q_terms;
     float *theta;                           // [n_queries] best known lower bound of each query's final k-th score:
                                             // read AND raised (atomicMax) by the scoring warps, see bm25_lean.cuh
+    float *const *peer_theta;               // device table of n_peers pointers: the same array on the other GPUs of a
+    int32_t n_peers;                        // doc-sharded corpus (peer memory over NVLink), raised together with ours
     float *part_s;                          // [n_queries][n_chunks_launch][K] per-item ranked lists
     int32_t *part_d;
     int32_t *counter;                       // work-item counter of this launch

@@ -22,10 +22,13 @@ oracle standing in as the checker).
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Callable
 
 import torch
 import torch.distributed as dist
+
+from . import _lib
 
 
 def shard_range(n_docs: int, rank: int, world: int) -> tuple[int, int]:
@@ -76,6 +79,58 @@ def exchange_thresholds(theta: torch.Tensor, group=None) -> None:
         dist.all_reduce(theta, op=dist.ReduceOp.MAX, group=group)
 
 
+class PeerThresholds:
+    """Per-query score bounds that the GPUs of one box raise in EACH OTHER's memory while they score
+    (include/probing_rag.h, pr_index_set_peer_thetas): this rank's array of 2 x capacity floats in
+    IPC-shareable device memory, every other rank's array opened over NVLink, and the pointer table the
+    kernels index.  One process per GPU; the 64-byte IPC handles travel through `all_gather_object`."""
+
+    def __init__(self, index, capacity: int, group=None):
+        L = _lib.lib()
+        self.index, self.group = index, group
+        self.capacity = int(capacity)
+        self.device = index.device
+        dev_no = self.device.index or 0
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        if world - 1 > _lib.PR_MAX_PEERS:
+            raise ValueError(f"at most {_lib.PR_MAX_PEERS + 1} ranks can share thresholds")
+        self._local = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        self._peers: list[ctypes.c_void_p] = []
+        with torch.cuda.device(self.device):
+            _lib.check(L.pr_peer_alloc(dev_no, 2 * self.capacity * 4, ctypes.byref(self._local), handle))
+            handles = [None] * world
+            dist.all_gather_object(handles, (rank, handle.raw), group=group)
+            for r, raw in handles:
+                if r == rank:
+                    continue
+                ptr = ctypes.c_void_p()
+                _lib.check(L.pr_peer_open(dev_no, raw, ctypes.byref(ptr)))
+                self._peers.append(ptr)
+            self._table = torch.zeros(2 * _lib.PR_MAX_PEERS, dtype=torch.int64, device=self.device)
+            bases = (ctypes.c_void_p * max(len(self._peers), 1))(*[p.value for p in self._peers])
+            _lib.check(L.pr_index_set_peer_thetas(index._handle, self._local, self.capacity, len(self._peers), bases,
+                                                  self._table.data_ptr()))
+        # nobody may raise a bound in an array that its owner has not initialised yet
+        dist.barrier(group=group)
+
+    def close(self) -> None:
+        L = _lib.lib()
+        if getattr(self, "_local", None) is None:
+            return
+        try:
+            torch.cuda.synchronize(self.device)
+            if dist.is_initialized():
+                dist.barrier(group=self.group)          # every rank has stopped writing into the others' arrays
+            with torch.cuda.device(self.device):
+                L.pr_index_set_peer_thetas(self.index._handle, None, 0, 0, None, None)
+                for p in self._peers:
+                    L.pr_peer_close(p)
+                L.pr_peer_free(self._local)
+        finally:
+            self._local, self._peers = None, []
+
+
 class ShardedBM25:
     """This rank's shard + the exchange steps.  `local_topk(q_indptr, q_terms, k) -> (scores, ids)`
     defaults to the shard's CUDA kernel (with the threshold exchange between its launches),
@@ -85,21 +140,40 @@ class ShardedBM25:
     doc_id_base = 0          # the merged lists carry global doc ids
 
     def __init__(self, index=None, group=None, local_topk: Callable | None = None,
-                 merge: Callable | None = None, exchange: bool = True):
+                 merge: Callable | None = None, exchange="allreduce", max_queries: int = 65536):
+        """exchange: how the shards tell each other their score bounds while a call runs --
+        "p2p": raised live in each other's memory by the scoring warps (NVLink peer memory, `PeerThresholds`;
+               batches of up to `max_queries` queries);
+        "allreduce" (or True): an all-reduce(MAX) between the launches of the call;
+        None / False: not at all (every shard filters with what it found itself)."""
         if index is None and local_topk is None:
             raise ValueError("pass the shard's BM25Index or a local_topk callable")
+        if exchange is True:
+            exchange = "allreduce"
+        if exchange not in ("p2p", "allreduce", None, False):
+            raise ValueError(f"exchange must be 'p2p', 'allreduce' or None, got {exchange!r}")
         self.index = index
         self.group = group
         self._local = local_topk
         self._merge = merge
         self._gath = {}
-        self._exchange = bool(exchange) and index is not None and local_topk is None and _world(group) > 1
+        real = index is not None and local_topk is None and _world(group) > 1
+        self.exchange = exchange if (real and exchange) else None
+        self._exchange = self.exchange == "allreduce"
+        self._peers = PeerThresholds(index, max_queries, group) if self.exchange == "p2p" else None
         self._max_docs = None
         if self._exchange:
             # every rank must join the same number of all-reduces per call: as many as the LONGEST shard has launches
             n = torch.tensor([index.n_docs], dtype=torch.int64, device=index.device)
             dist.all_reduce(n, op=dist.ReduceOp.MAX, group=group)
             self._max_docs = int(n.item())
+
+    def close(self) -> None:
+        """Release the peer-shared threshold arrays (collective: every rank calls it)."""
+        if self._peers is not None:
+            self._peers.close()
+            self._peers = None
+            self.exchange = None
 
     @property
     def n_docs_global(self) -> int:

@@ -27,7 +27,7 @@ TUNINGS = [
     dict(subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
     dict(subs_per_item=1, warps_per_cta=4, docs_per_launch=2048, min_items=1, items_per_warp=1),   # one sub-tile per item and launch: 49 launches
     dict(subs_per_item=5, warps_per_cta=12, docs_per_launch=1000000, min_items=100000),  # one launch
-    dict(subs_per_item=3, warps_per_cta=10, docs_per_launch=20000, min_items=2048),
+    dict(subs_per_item=3, warps_per_cta=12, docs_per_launch=20000, min_items=2048),
     dict(subs_per_item=24, warps_per_cta=8, items_per_warp=64),                           # items cut down to one sub-tile, one launch
     dict(subs_per_item=2, warps_per_cta=8, docs_per_launch=8192, min_items=1, items_per_warp=1),
     dict(subs_per_item=24, warps_per_cta=8, docs_per_launch=49152, min_items=1, items_per_warp=1),  # long items, 3 launches

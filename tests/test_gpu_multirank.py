@@ -35,18 +35,21 @@ def _worker(rank, world, port, out_dir):
         gi.set_tuning(subs_per_item=2, docs_per_launch=16384, min_items=1, items_per_warp=1)
         d_qi, d_qt = torch.from_numpy(qi).to(dev), torch.from_numpy(qt).to(dev)
         res = {}
-        for name, sb in (("exchange", ShardedBM25(gi)), ("plain", ShardedBM25(gi, exchange=False))):
-            for k in (10, 100):
+        for name, mode in (("p2p", "p2p"), ("exchange", "allreduce"), ("plain", None), ("p2p_again", "p2p")):
+            sb = ShardedBM25(gi, exchange=mode, max_queries=NQ)
+            assert sb.exchange == mode
+            for k in (10, 100, 10):                 # an odd number of calls: the next p2p instance starts on the other parity
                 s, d = sb.topk(d_qi, d_qt, k)
                 hs, hd, h2d, d2h = sb.topk_host(qi, qt, k)
                 torch.cuda.synchronize()
                 assert np.array_equal(hs, s.cpu().numpy()) and np.array_equal(hd, d.cpu().numpy())
                 assert d2h == NQ * k * 8
                 res[f"{name}_s{k}"], res[f"{name}_d{k}"] = hs, hd
+            sb.close()
         res["launches"] = np.array([gi.num_launches(NQ, 10)])
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), **res)
         with pytest.raises(ValueError):                 # bad term ids raise on the sharded path too
-            ShardedBM25(gi).topk(d_qi, torch.full_like(d_qt, VOCAB), 10)
+            ShardedBM25(gi, exchange="allreduce").topk(d_qi, torch.full_like(d_qt, VOCAB), 10)
     finally:
         dist.destroy_process_group()
 
@@ -72,6 +75,6 @@ def test_nccl_doc_shards_equal_single_index_and_oracle(tmp_path, world):
         for r in range(world):
             got = np.load(tmp_path / f"r{r}.npz")
             assert int(got["launches"][0]) > 2
-            for name in ("exchange", "plain"):
+            for name in ("p2p", "exchange", "plain", "p2p_again"):
                 assert np.array_equal(got[f"{name}_d{k}"], od), f"rank {r} {name}: merged doc ids differ (k={k})"
                 assert np.array_equal(got[f"{name}_s{k}"], os_), f"rank {r} {name}: merged scores differ (k={k})"

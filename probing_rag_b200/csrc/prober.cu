@@ -13,32 +13,52 @@
 // LayerNorm statistics, SiLU, softmax and fc3 (512->2) stay in fp32 on the CUDA cores.
 //
 // Kernels
-//   prober_ln_split_kernel   x fp32 -> LN_in -> (hi, lo) bf16, one warp per row
-//   prober_gemm_kernel<EPI>  one CTA = 128 rows x 512 columns of one prober:
-//        warp 0  TMA producer   A(hi,lo)[128x64] + B(hi,lo)[256x64] per stage, 128B swizzle
-//        warp 1  MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16, fp32 in TMEM
-//        warp 2  TMEM allocator (512 columns = the whole 128x512 fp32 accumulator)
-//        warps 4-7 epilogue     tcgen05.ld -> bias -> SiLU -> LN (3 passes over TMEM) ->
+//   prober_ln_split_kernel   x (f32 / bf16 / f16) -> LN_in -> (hi, lo) bf16, one warp per row
+//   prober_gemm_kernel<EPI>  a CTA PAIR (cluster of 2, the two SMs of a TPC) = 256 rows x 512 columns of one prober;
+//                            each CTA owns 128 rows and the whole 128x512 fp32 accumulator of them in its TMEM.
+//        warp 0  TMA producer   per k-block of 64: this CTA's A(hi,lo)[128x64] and HALF of B: for each 256-column
+//                               half of the output its 128 of the 256 weight rows (hi,lo) -- 96 KB per stage, 128B
+//                               swizzle, loaded with the cta_group::2 form that signals the leader CTA's barrier
+//        warp 1  MMA issuer     leader CTA only: tcgen05.mma.cta_group::2.kind::f16, M=256 N=256 K=16 -- every operand
+//                               byte is read from shared memory once per PAIR.  (With one CTA per tile the kernel
+//                               was bound by L2 -> SM operand traffic: bf16x3 doubles the operand bytes, and every
+//                               128-row tile re-read all of B: 192 KB per k-block, tensor pipe 41% busy.)
+//        warp 2  TMEM allocator (cta_group::2, 512 columns)
+//        warps 4-11 epilogue    tcgen05.ld -> bias -> SiLU -> LN (3 passes over TMEM) ->
 //                               EPI 1: (hi,lo) bf16 A2 to global; EPI 2: fc3 + softmax
 //   prober_gate_kernel + compaction kernels
 #include <cuda.h>
 #include <cuda_bf16.h>
+
+#include <mutex>
+#include <vector>
+
 #include <cuda_fp16.h>
 
 #include "common.cuh"
 
 namespace {
 
-constexpr int kBM = 128;       // rows per CTA
+constexpr int kBM = 128;       // rows per CTA (a CTA pair covers 256)
 constexpr int kBNH = 256;      // columns per MMA (half of the hidden size)
+constexpr int kBNC = kBNH / 2; // weight rows of one MMA that each CTA of the pair holds
 constexpr int kBK = 64;        // K elements per stage (128 bytes of bf16 = one swizzle row)
 constexpr int kHidden = 512;
 constexpr int kStages = 2;
-constexpr int kAStageBytes = kBM * kBK * 2;    // 16 KB
-constexpr int kBStageBytes = kBNH * kBK * 2;   // 32 KB
-constexpr int kStageBytes = 2 * kAStageBytes + 2 * kBStageBytes;  // A_hi A_lo B_hi B_lo = 96 KB
-constexpr int kGemmThreads = 384;  // warps 0-2: TMA / MMA / TMEM alloc, warp 3 idle, warps 4-11: epilogue
-constexpr int kEpiThreads = 256;   // two epilogue threads per row: columns [0,256) and [256,512)
+constexpr int kTileBytes = kBM * kBK * 2;      // every operand tile is 128 rows x 64 k of bf16 = 16 KB
+// stage: A_hi A_lo | B_hi(half 0) B_hi(half 1) | B_lo(half 0) B_lo(half 1)
+constexpr int kStageBytes = 6 * kTileBytes;    // 96 KB
+static_assert(kBNC == kBM, "operand tiles share one box shape");
+#ifndef PR_EPI_SPLIT
+#define PR_EPI_SPLIT 2
+#endif
+// Epilogue threads per row, each owning kHidden / kEpiSplit columns.  4 (16 warps, 96 registers) was measured equal to
+// 2 (8 warps, 120 / 168 registers) at 16,384 rows: the shorter epilogue is paid back by the input-LayerNorm blocks of
+// the next prober no longer fitting beside the GEMM CTA (profiles/r02/prober_history.md).
+constexpr int kEpiSplit = PR_EPI_SPLIT;
+constexpr int kEpiThreads = 128 * kEpiSplit;
+constexpr int kGemmThreads = 128 + kEpiThreads;    // warps 0-2: TMA / MMA / TMEM alloc, warp 3 idle, then the epilogue
+constexpr int kEpiCols = kHidden / kEpiSplit;
 constexpr float kLnEps = 1e-5f;
 
 // ------------------------------------------------------------------------------ PTX wrappers
@@ -67,43 +87,61 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
             : "memory");
     } while (!done);
 }
-__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
+// shared::cluster address of a barrier of the PAIR'S LEADER (even CTA): the same offset with the peer bit cleared
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+// TMA load into THIS CTA's shared memory whose completion bytes are counted by the leader CTA's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
 {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
             smem_u32(smem_dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
         : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t cols)
 {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(cols)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(cols)
                  : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols)
 {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, single-CTA group
+// D[tmem of both CTAs] (+)= A[smem of both CTAs: 128 rows each] * B[smem of both CTAs: N/2 rows each], bf16 x bf16 -> fp32;
+// issued by one thread of the leader CTA, the descriptors are offsets valid in both CTAs' shared memory
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(d_tmem),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// arrive on an mbarrier once every tcgen05.mma issued so far by this thread has completed
-__device__ __forceinline__ void umma_commit(uint64_t *bar)
+// arrive on the barrier at this offset in BOTH CTAs of the pair once every tcgen05.mma issued so far has completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar)
 {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
 {
@@ -144,10 +182,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
     d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
     return d;
 }
-// cute::UMMA::InstrDescriptor: fp32 accumulate, bf16 x bf16, both K-major, M=128, N=256
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBNH >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+// cute::UMMA::InstrDescriptor: fp32 accumulate, bf16 x bf16, both K-major, M=256 (the pair), N=256
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBNH >> 3) << 17) | ((uint32_t)((2 * kBM) >> 4) << 24);
 
-__device__ __forceinline__ float silu(float v) { return v / (1.f + expf(-v)); }
+// SiLU with the SFU exponential and reciprocal (2 ulp each: ~1e-7 on the activations, against a 1e-3 bar on the
+// probabilities); the accurate expf + IEEE division were a quarter of the epilogue's instructions
+__device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.f + __expf(-v)); }
 
 __device__ __forceinline__ void split_bf16(float y, __nv_bfloat16 &hi, __nv_bfloat16 &lo)
 {
@@ -179,57 +219,59 @@ __device__ __forceinline__ float4 load_x4<__half>(const __half *x, int i)
     return make_float4(a.x, a.y, b.x, b.y);
 }
 
+// Register-light on purpose (<= 64 registers, 128 threads per block): in the per-prober pipeline these blocks run
+// NEXT TO a GEMM CTA on the same SM (which leaves ~19k registers and no shared memory), so the row is not kept in
+// registers between the passes -- the second and third pass re-read it (8 KB per warp, L2 hits; X comes from HBM once).
+constexpr int kLnThreads = 128;
 template <typename T>
-__global__ void __launch_bounds__(256) prober_ln_split_kernel(const T *__restrict__ X, const float *__restrict__ gamma,
-                                                              const float *__restrict__ beta, __nv_bfloat16 *__restrict__ a_hi,
-                                                              __nv_bfloat16 *__restrict__ a_lo, int n_rows, int rows_pad,
-                                                              int n_probers, int d_model)
+__global__ void __launch_bounds__(kLnThreads, 8) prober_ln_split_kernel(const T *__restrict__ X, const float *__restrict__ gamma,
+                                                                       const float *__restrict__ beta, __nv_bfloat16 *__restrict__ a_hi,
+                                                                       __nv_bfloat16 *__restrict__ a_lo, int n_rows, int rows_pad,
+                                                                       int n_probers, int d_model, int p0, int np)
 {
     const int lane = threadIdx.x & 31;
     const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (wid >= (int64_t)n_rows * n_probers) return;
-    const int row = (int)(wid / n_probers), p = (int)(wid % n_probers);
+    if (wid >= (int64_t)n_rows * np) return;
+    const int row = (int)(wid / np), p = p0 + (int)(wid % np);   // probers [p0, p0 + np) of every row
     const T *xrow = X + ((size_t)row * n_probers + p) * d_model;
     const int nv = d_model >> 7;  // 4-feature groups per lane (16 for d_model = 2048)
-    float4 v[16];
     float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-        if (i < nv) {
-            v[i] = load_x4<T>(xrow, lane + 32 * i);
-            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-        }
+#pragma unroll 4
+    for (int i = 0; i < nv; ++i) {
+        const float4 v = load_x4<T>(xrow, lane + 32 * i);
+        sum += (v.x + v.y) + (v.z + v.w);
+    }
     for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(PR_FULL_MASK, sum, o);
     const float mean = sum / (float)d_model;
     float sq = 0.f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-        if (i < nv) {
-            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-            sq += (a * a + b * b) + (c * c + d * d);
-        }
+#pragma unroll 4
+    for (int i = 0; i < nv; ++i) {
+        const float4 v = load_x4<T>(xrow, lane + 32 * i);
+        const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+        sq += (a * a + b * b) + (c * c + d * d);
+    }
     for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(PR_FULL_MASK, sq, o);
     const float rstd = rsqrtf(sq / (float)d_model + kLnEps);
     const float4 *g4 = reinterpret_cast<const float4 *>(gamma + (size_t)p * d_model);
     const float4 *b4 = reinterpret_cast<const float4 *>(beta + (size_t)p * d_model);
     const size_t out_row = ((size_t)p * rows_pad + row) * d_model;
+#pragma unroll 2
+    for (int i = 0; i < nv; ++i) {
+        const float4 v = load_x4<T>(xrow, lane + 32 * i);
+        const float4 g = g4[lane + 32 * i], b = b4[lane + 32 * i];
+        const float y[4] = {(v.x - mean) * rstd * g.x + b.x, (v.y - mean) * rstd * g.y + b.y,
+                            (v.z - mean) * rstd * g.z + b.z, (v.w - mean) * rstd * g.w + b.w};
+        __nv_bfloat16 h[4], l[4];
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
-        if (i < nv) {
-            const float4 g = g4[lane + 32 * i], b = b4[lane + 32 * i];
-            const float y[4] = {(v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
-                                (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w};
-            __nv_bfloat16 h[4], l[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) split_bf16(y[k], h[k], l[k]);
-            const size_t o = out_row + (size_t)(lane + 32 * i) * 4;
-            const uint2 hv = make_uint2((uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16),
-                                        (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16));
-            const uint2 lv = make_uint2((uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16),
-                                        (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16));
-            *reinterpret_cast<uint2 *>(a_hi + o) = hv;
-            *reinterpret_cast<uint2 *>(a_lo + o) = lv;
-        }
+        for (int k = 0; k < 4; ++k) split_bf16(y[k], h[k], l[k]);
+        const size_t o = out_row + (size_t)(lane + 32 * i) * 4;
+        const uint2 hv = make_uint2((uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16),
+                                    (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16));
+        const uint2 lv = make_uint2((uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16),
+                                    (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16));
+        *reinterpret_cast<uint2 *>(a_hi + o) = hv;
+        *reinterpret_cast<uint2 *>(a_lo + o) = lv;
+    }
 }
 
 // ------------------------------------------------------------------ GEMM + fused epilogue
@@ -242,12 +284,13 @@ struct GemmArgs {
     float *logits;                    // [rows][P][2] or null         (EPI 2)
     float *probs;                     // [rows][P][2]                 (EPI 2)
     int n_probers;
+    int p0;                           // first prober of this launch (blockIdx.y counts from it)
 };
 
 constexpr size_t kGemmSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 5 * kHidden * 4 + 256 + 4 * kEpiThreads * 4;
 
 template <int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 prober_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                    const GemmArgs g)
@@ -266,13 +309,14 @@ prober_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     float *s_red = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(full_bar) + 256);  // [4][kEpiThreads] row partials
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int p = blockIdx.y;                 // prober
-    const int row0 = blockIdx.x * kBM;        // first row of this tile
-    const int n_iter = (g.K / kBK) * 2;       // (k-block, column half) pairs
+    const int p = g.p0 + blockIdx.y;          // prober
+    const int row0 = blockIdx.x * kBM;        // first row of this CTA's tile (the pair: blockIdx.x even and odd)
+    const uint32_t cta_rank = cluster_ctarank();
+    const int n_iter = g.K / kBK;             // k-blocks
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], 1);       // (used in the leader CTA only: its producer's arrive + both CTAs' bytes)
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(acc_bar, 1);
@@ -293,89 +337,104 @@ prober_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         }
     }
     tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
+    cluster_sync();   // both CTAs: barriers initialised, TMEM allocated (the peer's TMA completions and the leader's
+    tc_fence_after(); // MMAs touch the other CTA's barriers / TMEM)
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0 && lane == 0) {
-        // ===== TMA producer
+        // ===== TMA producer (both CTAs): this CTA's A rows and its half of the weight rows of either column half.
+        // Completion bytes of BOTH CTAs are counted by the leader's full barrier, which only the leader arms.
         for (int it = 0; it < n_iter; ++it) {
             const int s = it % kStages;
             const uint32_t ph = (uint32_t)(it / kStages) & 1u;
             mbar_wait(&empty_bar[s], ph ^ 1u);
             unsigned char *st = stage_base + (size_t)s * kStageBytes;
-            const int kb = it >> 1, nh = it & 1;
-            mbar_expect_tx(&full_bar[s], kStageBytes);
-            tma_load_2d(st, &map_a_hi, &full_bar[s], kb * kBK, p * g.rows_pad + row0);
-            tma_load_2d(st + kAStageBytes, &map_a_lo, &full_bar[s], kb * kBK, p * g.rows_pad + row0);
-            tma_load_2d(st + 2 * kAStageBytes, &map_b_hi, &full_bar[s], kb * kBK, p * kHidden + nh * kBNH);
-            tma_load_2d(st + 2 * kAStageBytes + kBStageBytes, &map_b_lo, &full_bar[s], kb * kBK, p * kHidden + nh * kBNH);
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * kStageBytes);
+            const int a_row = p * g.rows_pad + row0, b_row = p * kHidden + (int)cta_rank * kBNC;
+            tma_load_2d_pair(st, &map_a_hi, &full_bar[s], it * kBK, a_row);
+            tma_load_2d_pair(st + kTileBytes, &map_a_lo, &full_bar[s], it * kBK, a_row);
+            tma_load_2d_pair(st + 2 * kTileBytes, &map_b_hi, &full_bar[s], it * kBK, b_row);
+            tma_load_2d_pair(st + 3 * kTileBytes, &map_b_hi, &full_bar[s], it * kBK, b_row + kBNH);
+            tma_load_2d_pair(st + 4 * kTileBytes, &map_b_lo, &full_bar[s], it * kBK, b_row);
+            tma_load_2d_pair(st + 5 * kTileBytes, &map_b_lo, &full_bar[s], it * kBK, b_row + kBNH);
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===== MMA issuer: acc[:, nh*256 .. +256) += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo
+    } else if (warp == 1 && lane == 0 && cta_rank == 0) {
+        // ===== MMA issuer (leader CTA): acc[256 rows, nh*256 .. +256) += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo
         for (int it = 0; it < n_iter; ++it) {
             const int s = it % kStages;
             const uint32_t ph = (uint32_t)(it / kStages) & 1u;
             mbar_wait(&full_bar[s], ph);
             tc_fence_after();
             const uint32_t st = smem_u32(stage_base + (size_t)s * kStageBytes);
-            const int kb = it >> 1, nh = it & 1;
-            const uint32_t d_tmem = tmem_base + (uint32_t)(nh * kBNH);
-            const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kAStageBytes);
-            const uint64_t b_hi = umma_desc_sw128(st + 2 * kAStageBytes);
-            const uint64_t b_lo = umma_desc_sw128(st + 2 * kAStageBytes + kBStageBytes);
+            const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kTileBytes);
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-                const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);  // 32 bytes per K=16 step, 16-byte units
-                umma_bf16(d_tmem, a_hi + adv, b_hi + adv, kIdesc, (kb | k) ? 1u : 0u);
-                umma_bf16(d_tmem, a_lo + adv, b_hi + adv, kIdesc, 1u);
-                umma_bf16(d_tmem, a_hi + adv, b_lo + adv, kIdesc, 1u);
+            for (int nh = 0; nh < 2; ++nh) {
+                const uint32_t d_tmem = tmem_base + (uint32_t)(nh * kBNH);
+                const uint64_t b_hi = umma_desc_sw128(st + (2 + nh) * kTileBytes), b_lo = umma_desc_sw128(st + (4 + nh) * kTileBytes);
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k) {
+                    const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);  // 32 bytes per K=16 step, 16-byte units
+                    umma_bf16(d_tmem, a_hi + adv, b_hi + adv, kIdesc, (it | k) ? 1u : 0u);
+                    umma_bf16(d_tmem, a_lo + adv, b_hi + adv, kIdesc, 1u);
+                    umma_bf16(d_tmem, a_hi + adv, b_lo + adv, kIdesc, 1u);
+                }
             }
-            umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+            umma_commit_pair(&empty_bar[s]);  // frees the stage in both CTAs once these MMAs have read it
         }
-        umma_commit(acc_bar);            // accumulator complete
+        umma_commit_pair(acc_bar);            // accumulators complete (both CTAs' epilogues wait on their own copy)
     } else if (warp >= 4) {
-        // ===== epilogue: TMEM lane t = row row0+t is shared by two threads (warps w and w+4 see the same lane
-        // quadrant): thread (half, t) owns columns [half*256, half*256+256) and the row statistics are combined
-        // through shared memory (always half 0 + half 1, so both threads hold identical values)
+        // ===== epilogue: TMEM lane t = row row0+t is shared by kEpiSplit threads (warps w, w+4, w+8, .. see the same
+        // lane quadrant): thread (part, t) owns columns [part * kEpiCols, +kEpiCols) and the row statistics are combined
+        // through shared memory (every thread of a row sums the parts in the same order: identical values)
         mbar_wait(acc_bar, 0);
         tc_fence_after();
         const int et = threadIdx.x - 128;
-        const int half = et >> 7, t = et & 127;
+        const int part = et >> 7, t = et & 127;
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         const int row = row0 + t;
-        const int cb = half * (kHidden / 2), ce = cb + kHidden / 2;
+        const int cb = part * kEpiCols, ce = cb + kEpiCols;
         auto epi_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); };
         uint32_t r[32];
-        // pass 1: bias + SiLU, keep the activations in TMEM, row sum
-        float sum = 0.f;
+        // pass 1: bias + SiLU, keep the activations in TMEM; row mean and centred second moment in the same pass:
+        // exact two-pass statistics of every 32-column chunk while it sits in registers, chunks (and then the parts
+        // of the row) merged with Chan's formula -- no second sweep over TMEM, no E[x^2] - mean^2 cancellation
+        float run_mean = 0.f, run_m2 = 0.f;
         for (int c0 = cb; c0 < ce; c0 += 32) {
             tmem_ld32(taddr + c0, r);
+            float csum = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const float a = silu(__uint_as_float(r[j]) + s_bias[c0 + j]);
-                sum += a;
+                csum += a;
                 r[j] = __float_as_uint(a);
             }
             tmem_st32(taddr + c0, r);
-        }
-        s_red[et] = sum;
-        epi_sync();
-        const float mean = (s_red[t] + s_red[128 + t]) * (1.f / kHidden);
-        // pass 2: centred second moment (torch.nn.LayerNorm: biased variance)
-        float sq = 0.f;
-        for (int c0 = cb; c0 < ce; c0 += 32) {
-            tmem_ld32(taddr + c0, r);
+            const float cmean = csum * (1.f / 32.f);
+            float cm2 = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const float d = __uint_as_float(r[j]) - mean;
-                sq += d * d;
+                const float d = __uint_as_float(r[j]) - cmean;
+                cm2 = fmaf(d, d, cm2);
             }
+            const float n_a = (float)(c0 - cb), n_ab = n_a + 32.f, delta = cmean - run_mean;
+            run_mean += delta * (32.f / n_ab);
+            run_m2 += cm2 + delta * delta * (n_a * 32.f / n_ab);
         }
-        s_red[kEpiThreads + et] = sq;
+        s_red[et] = run_mean;
+        s_red[kEpiThreads + et] = run_m2;
         epi_sync();
-        const float rstd = rsqrtf((s_red[kEpiThreads + t] + s_red[kEpiThreads + 128 + t]) * (1.f / kHidden) + kLnEps);
-        // pass 3: normalise; EPI 1 writes the split bf16 operand of fc2, EPI 2 applies fc3 + softmax
+        // equal-sized parts: mean = average of the part means, M2 = sum M2_i + kEpiCols * sum (mean_i - mean)^2
+        float mean = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < kEpiSplit; ++i) mean += s_red[i * 128 + t];
+        mean *= 1.f / kEpiSplit;
+#pragma unroll
+        for (int i = 0; i < kEpiSplit; ++i) {
+            const float d = s_red[i * 128 + t] - mean;
+            m2 += s_red[kEpiThreads + i * 128 + t] + d * d * (float)kEpiCols;
+        }
+        const float rstd = rsqrtf(m2 * (1.f / kHidden) + kLnEps);   // torch.nn.LayerNorm: biased variance
+        // pass 2: normalise; EPI 1 writes the split bf16 operand of fc2, EPI 2 applies fc3 + softmax
         float z0 = 0.f, z1 = 0.f;
         for (int c0 = cb; c0 < ce; c0 += 32) {
             tmem_ld32(taddr + c0, r);
@@ -413,9 +472,15 @@ prober_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             s_red[2 * kEpiThreads + et] = z0;
             s_red[3 * kEpiThreads + et] = z1;
             epi_sync();
-            if (half == 0 && row < g.n_rows) {
-                z0 = (s_red[2 * kEpiThreads + t] + s_red[2 * kEpiThreads + 128 + t]) + g.b3[p * 2 + 0];
-                z1 = (s_red[3 * kEpiThreads + t] + s_red[3 * kEpiThreads + 128 + t]) + g.b3[p * 2 + 1];
+            if (part == 0 && row < g.n_rows) {
+                z0 = z1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < kEpiSplit; ++i) {
+                    z0 += s_red[2 * kEpiThreads + i * 128 + t];
+                    z1 += s_red[3 * kEpiThreads + i * 128 + t];
+                }
+                z0 += g.b3[p * 2 + 0];
+                z1 += g.b3[p * 2 + 1];
                 const size_t o = ((size_t)row * g.n_probers + p) * 2;
                 if (g.logits) {
                     g.logits[o] = z0;
@@ -430,7 +495,7 @@ prober_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         }
         tc_fence_before();
     }
-    __syncthreads();
+    cluster_sync();   // neither CTA may free TMEM (or exit) while the pair's MMAs or loads can still touch it
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
@@ -540,7 +605,7 @@ struct ProberLayout {
 ProberLayout prober_layout(int P, int n_rows, int d_model, int hidden)
 {
     ProberLayout l;
-    l.rows_pad = (n_rows + kBM - 1) / kBM * kBM;
+    l.rows_pad = (n_rows + 2 * kBM - 1) / (2 * kBM) * (2 * kBM);   // whole CTA pairs
     size_t o = 0;
     l.a1_hi = o; o = up(o + (size_t)P * l.rows_pad * d_model * 2, 1024);
     l.a1_lo = o; o = up(o + (size_t)P * l.rows_pad * d_model * 2, 1024);
@@ -550,6 +615,37 @@ ProberLayout prober_layout(int P, int n_rows, int d_model, int hidden)
     l.block_cnt = o; o = up(o + ((size_t)n_rows / 256 + 2) * 4, 256);
     l.total = o;
     return l;
+}
+
+// Side stream + events of the per-prober pipeline, one set per (device, caller stream), created on first use and
+// kept for the life of the process (streams and events, not device memory).
+struct ProberSide {
+    int device;
+    cudaStream_t caller, stream;
+    cudaEvent_t fork, ln_done[PR_PROBER_MAX];
+};
+
+ProberSide *prober_side(cudaStream_t caller)
+{
+    static std::mutex mu;
+    static std::vector<ProberSide *> all;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    for (ProberSide *s : all)
+        if (s->device == dev && s->caller == caller) return s;
+    ProberSide *s = new ProberSide();
+    s->device = dev;
+    s->caller = caller;
+    bool ok = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i < PR_PROBER_MAX; ++i) ok = cudaEventCreateWithFlags(&s->ln_done[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {  // no side stream: the caller falls back to the single-stream order
+        delete s;
+        return nullptr;
+    }
+    all.push_back(s);
+    return s;
 }
 
 }  // namespace
@@ -611,35 +707,23 @@ extern "C" int pr_prober_forward(const pr_prober_set_t *ps, int32_t n_rows, cons
     float *probs = (float *)(ws + l.probs);
     int32_t *block_cnt = (int32_t *)(ws + l.block_cnt);
 
-    // kernel 0: LN_in + split
-    {
-        const int64_t warps = (int64_t)n_rows * P;
-        const unsigned nb = (unsigned)((warps + 7) / 8);
-        if (x_dtype == 0)
-            prober_ln_split_kernel<float><<<nb, 256, 0, st>>>((const float *)X_dev, ps->ln_in_w, ps->ln_in_b, a1_hi, a1_lo, n_rows,
-                                                              l.rows_pad, P, ps->d_model);
-        else if (x_dtype == 1)
-            prober_ln_split_kernel<__nv_bfloat16><<<nb, 256, 0, st>>>((const __nv_bfloat16 *)X_dev, ps->ln_in_w, ps->ln_in_b, a1_hi,
-                                                                      a1_lo, n_rows, l.rows_pad, P, ps->d_model);
-        else
-            prober_ln_split_kernel<__half><<<nb, 256, 0, st>>>((const __half *)X_dev, ps->ln_in_w, ps->ln_in_b, a1_hi, a1_lo, n_rows,
-                                                               l.rows_pad, P, ps->d_model);
-        PR_CUDA_CHECK(cudaGetLastError());
-    }
     CUtensorMap m_a1h, m_a1l, m_w1h, m_w1l, m_a2h, m_a2l, m_w2h, m_w2l;
     int rc;
     if ((rc = make_map(&m_a1h, a1_hi, (uint64_t)P * l.rows_pad, ps->d_model, kBM)) != PR_OK) return rc;
     if ((rc = make_map(&m_a1l, a1_lo, (uint64_t)P * l.rows_pad, ps->d_model, kBM)) != PR_OK) return rc;
-    if ((rc = make_map(&m_w1h, ps->w1_hi, (uint64_t)P * kHidden, ps->d_model, kBNH)) != PR_OK) return rc;
-    if ((rc = make_map(&m_w1l, ps->w1_lo, (uint64_t)P * kHidden, ps->d_model, kBNH)) != PR_OK) return rc;
+    if ((rc = make_map(&m_w1h, ps->w1_hi, (uint64_t)P * kHidden, ps->d_model, kBNC)) != PR_OK) return rc;
+    if ((rc = make_map(&m_w1l, ps->w1_lo, (uint64_t)P * kHidden, ps->d_model, kBNC)) != PR_OK) return rc;
     if ((rc = make_map(&m_a2h, a2_hi, (uint64_t)P * l.rows_pad, kHidden, kBM)) != PR_OK) return rc;
     if ((rc = make_map(&m_a2l, a2_lo, (uint64_t)P * l.rows_pad, kHidden, kBM)) != PR_OK) return rc;
-    if ((rc = make_map(&m_w2h, ps->w2_hi, (uint64_t)P * kHidden, kHidden, kBNH)) != PR_OK) return rc;
-    if ((rc = make_map(&m_w2l, ps->w2_lo, (uint64_t)P * kHidden, kHidden, kBNH)) != PR_OK) return rc;
+    if ((rc = make_map(&m_w2h, ps->w2_hi, (uint64_t)P * kHidden, kHidden, kBNC)) != PR_OK) return rc;
+    if ((rc = make_map(&m_w2l, ps->w2_lo, (uint64_t)P * kHidden, kHidden, kBNC)) != PR_OK) return rc;
 
-    PR_CUDA_CHECK(cudaFuncSetAttribute(prober_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
-    PR_CUDA_CHECK(cudaFuncSetAttribute(prober_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
-    const dim3 grid((unsigned)(l.rows_pad / kBM), (unsigned)P);
+    static bool attr_done = false;  // (idempotent; a race only repeats the call)
+    if (!attr_done) {
+        PR_CUDA_CHECK(cudaFuncSetAttribute(prober_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
+        PR_CUDA_CHECK(cudaFuncSetAttribute(prober_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
+        attr_done = true;
+    }
     GemmArgs g;
     g.n_rows = n_rows;
     g.rows_pad = l.rows_pad;
@@ -650,20 +734,62 @@ extern "C" int pr_prober_forward(const pr_prober_set_t *ps, int32_t n_rows, cons
     g.out_lo = a2_lo;
     g.logits = out_logits_dev;
     g.probs = probs;
-    // kernel 1: fc1 + SiLU + LN1 -> split operand of fc2
-    g.K = ps->d_model;
-    g.bias = ps->b1;
-    g.ln_w = ps->ln1_w;
-    g.ln_b = ps->ln1_b;
-    prober_gemm_kernel<1><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(m_a1h, m_a1l, m_w1h, m_w1l, g);
-    PR_CUDA_CHECK(cudaGetLastError());
-    // kernel 2: fc2 + SiLU + LN2 + fc3 + softmax
-    g.K = kHidden;
-    g.bias = ps->b2;
-    g.ln_w = ps->ln2_w;
-    g.ln_b = ps->ln2_b;
-    prober_gemm_kernel<2><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(m_a2h, m_a2l, m_w2h, m_w2l, g);
-    PR_CUDA_CHECK(cudaGetLastError());
+
+    auto launch_ln = [&](cudaStream_t s, int p0, int np) -> int {
+        const int64_t warps = (int64_t)n_rows * np;
+        const unsigned nb = (unsigned)((warps + kLnThreads / 32 - 1) / (kLnThreads / 32));
+        if (x_dtype == 0)
+            prober_ln_split_kernel<float><<<nb, kLnThreads, 0, s>>>((const float *)X_dev, ps->ln_in_w, ps->ln_in_b, a1_hi, a1_lo, n_rows,
+                                                             l.rows_pad, P, ps->d_model, p0, np);
+        else if (x_dtype == 1)
+            prober_ln_split_kernel<__nv_bfloat16><<<nb, kLnThreads, 0, s>>>((const __nv_bfloat16 *)X_dev, ps->ln_in_w, ps->ln_in_b, a1_hi,
+                                                                     a1_lo, n_rows, l.rows_pad, P, ps->d_model, p0, np);
+        else
+            prober_ln_split_kernel<__half><<<nb, kLnThreads, 0, s>>>((const __half *)X_dev, ps->ln_in_w, ps->ln_in_b, a1_hi, a1_lo, n_rows,
+                                                              l.rows_pad, P, ps->d_model, p0, np);
+        PR_CUDA_CHECK(cudaGetLastError());
+        return PR_OK;
+    };
+    auto launch_gemms = [&](int p0, int np) -> int {
+        const dim3 grid((unsigned)(l.rows_pad / kBM), (unsigned)np);
+        g.p0 = p0;
+        // fc1 + SiLU + LN1 -> split operand of fc2
+        g.K = ps->d_model;
+        g.bias = ps->b1;
+        g.ln_w = ps->ln1_w;
+        g.ln_b = ps->ln1_b;
+        prober_gemm_kernel<1><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(m_a1h, m_a1l, m_w1h, m_w1l, g);
+        // fc2 + SiLU + LN2 + fc3 + softmax
+        g.K = kHidden;
+        g.bias = ps->b2;
+        g.ln_w = ps->ln2_w;
+        g.ln_b = ps->ln2_b;
+        prober_gemm_kernel<2><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(m_a2h, m_a2l, m_w2h, m_w2l, g);
+        PR_CUDA_CHECK(cudaGetLastError());
+        return PR_OK;
+    };
+
+    ProberSide *side = (P > 1 && (int64_t)n_rows * P >= 8192) ? prober_side(st) : nullptr;
+    if (!side) {
+        // small batch: LN of all probers, then both GEMMs over all probers, on the caller's stream
+        if ((rc = launch_ln(st, 0, P)) != PR_OK) return rc;
+        if ((rc = launch_gemms(0, P)) != PR_OK) return rc;
+    } else {
+        // Large batch: one prober at a time.  The input LayerNorm is HBM-bound (it reads X and writes the split
+        // operand: 1.6 GB at 16,384 rows, a quarter of the call when run in front of the GEMMs) and the GEMMs are
+        // tensor/L2-bound, so LN of prober p+1 runs on a side stream WHILE the GEMMs of prober p run.  One prober's
+        // row tiles (128 at 16,384 rows) are one wave of the 148 SMs, so launching per prober costs no extra rounds.
+        PR_CUDA_CHECK(cudaEventRecord(side->fork, st));
+        PR_CUDA_CHECK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        for (int p = 0; p < P; ++p) {
+            if ((rc = launch_ln(side->stream, p, 1)) != PR_OK) return rc;
+            PR_CUDA_CHECK(cudaEventRecord(side->ln_done[p], side->stream));
+        }
+        for (int p = 0; p < P; ++p) {
+            PR_CUDA_CHECK(cudaStreamWaitEvent(st, side->ln_done[p], 0));
+            if ((rc = launch_gemms(p, 1)) != PR_OK) return rc;
+        }
+    }
     // gate + ordered compaction of the rows that retrieve
     const int nb = (n_rows + 255) / 256;
     PR_CUDA_CHECK(cudaMemsetAsync(out_compact_idx_dev, 0xff, (size_t)n_rows * 4, st));  // entries past n_retrieve read -1

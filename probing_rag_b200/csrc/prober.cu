@@ -30,8 +30,6 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
-#include <mutex>
-#include <vector>
 
 #include <cuda_fp16.h>
 
@@ -219,9 +217,9 @@ __device__ __forceinline__ float4 load_x4<__half>(const __half *x, int i)
     return make_float4(a.x, a.y, b.x, b.y);
 }
 
-// Register-light on purpose (<= 64 registers, 128 threads per block): in the per-prober pipeline these blocks run
-// NEXT TO a GEMM CTA on the same SM (which leaves ~19k registers and no shared memory), so the row is not kept in
-// registers between the passes -- the second and third pass re-read it (8 KB per warp, L2 hits; X comes from HBM once).
+// Register-light (<= 64 registers, 128 threads per block): the row is not kept in registers between the passes -- the
+// second and third pass re-read it (8 KB per warp, L1/L2 hits; X comes from HBM once).  Same speed as holding the row
+// (HBM-bound either way: 1.6 GB at 16,384 rows x 6), half the registers.
 constexpr int kLnThreads = 128;
 template <typename T>
 __global__ void __launch_bounds__(kLnThreads, 8) prober_ln_split_kernel(const T *__restrict__ X, const float *__restrict__ gamma,
@@ -617,37 +615,6 @@ ProberLayout prober_layout(int P, int n_rows, int d_model, int hidden)
     return l;
 }
 
-// Side stream + events of the per-prober pipeline, one set per (device, caller stream), created on first use and
-// kept for the life of the process (streams and events, not device memory).
-struct ProberSide {
-    int device;
-    cudaStream_t caller, stream;
-    cudaEvent_t fork, ln_done[PR_PROBER_MAX];
-};
-
-ProberSide *prober_side(cudaStream_t caller)
-{
-    static std::mutex mu;
-    static std::vector<ProberSide *> all;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-    std::lock_guard<std::mutex> lock(mu);
-    for (ProberSide *s : all)
-        if (s->device == dev && s->caller == caller) return s;
-    ProberSide *s = new ProberSide();
-    s->device = dev;
-    s->caller = caller;
-    bool ok = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) == cudaSuccess;
-    for (int i = 0; ok && i < PR_PROBER_MAX; ++i) ok = cudaEventCreateWithFlags(&s->ln_done[i], cudaEventDisableTiming) == cudaSuccess;
-    if (!ok) {  // no side stream: the caller falls back to the single-stream order
-        delete s;
-        return nullptr;
-    }
-    all.push_back(s);
-    return s;
-}
-
 }  // namespace
 
 extern "C" size_t pr_prober_workspace_bytes(int32_t n_probers, int32_t n_rows, int32_t d_model, int32_t hidden)
@@ -769,27 +736,11 @@ extern "C" int pr_prober_forward(const pr_prober_set_t *ps, int32_t n_rows, cons
         return PR_OK;
     };
 
-    ProberSide *side = (P > 1 && (int64_t)n_rows * P >= 8192) ? prober_side(st) : nullptr;
-    if (!side) {
-        // small batch: LN of all probers, then both GEMMs over all probers, on the caller's stream
-        if ((rc = launch_ln(st, 0, P)) != PR_OK) return rc;
-        if ((rc = launch_gemms(0, P)) != PR_OK) return rc;
-    } else {
-        // Large batch: one prober at a time.  The input LayerNorm is HBM-bound (it reads X and writes the split
-        // operand: 1.6 GB at 16,384 rows, a quarter of the call when run in front of the GEMMs) and the GEMMs are
-        // tensor/L2-bound, so LN of prober p+1 runs on a side stream WHILE the GEMMs of prober p run.  One prober's
-        // row tiles (128 at 16,384 rows) are one wave of the 148 SMs, so launching per prober costs no extra rounds.
-        PR_CUDA_CHECK(cudaEventRecord(side->fork, st));
-        PR_CUDA_CHECK(cudaStreamWaitEvent(side->stream, side->fork, 0));
-        for (int p = 0; p < P; ++p) {
-            if ((rc = launch_ln(side->stream, p, 1)) != PR_OK) return rc;
-            PR_CUDA_CHECK(cudaEventRecord(side->ln_done[p], side->stream));
-        }
-        for (int p = 0; p < P; ++p) {
-            PR_CUDA_CHECK(cudaStreamWaitEvent(st, side->ln_done[p], 0));
-            if ((rc = launch_gemms(p, 1)) != PR_OK) return rc;
-        }
-    }
+    // LN of all probers, then both GEMMs over all probers, on the caller's stream.  (Measured and dropped: running the
+    // HBM-bound input LayerNorm of prober p+1 on a side stream while the GEMMs of prober p run -- no gain at 16,384
+    // rows, the GEMMs slow down by what the overlap saves, and per-prober launches cost mid-size batches 4x.)
+    if ((rc = launch_ln(st, 0, P)) != PR_OK) return rc;
+    if ((rc = launch_gemms(0, P)) != PR_OK) return rc;
     // gate + ordered compaction of the rows that retrieve
     const int nb = (n_rows + 255) / 256;
     PR_CUDA_CHECK(cudaMemsetAsync(out_compact_idx_dev, 0xff, (size_t)n_rows * 4, st));  // entries past n_retrieve read -1

@@ -176,21 +176,26 @@ int pr_topk_merge(int32_t n_queries, int32_t k, int32_t n_lists, const float *sc
  * (/root/reference/exp_rag.py:407-415) + stream compaction of the "retrieve" rows. */
 #define PR_PROBER_MAX 8
 
-/* A set of n_probers ImprovedProbe MLPs, packed per prober and kept in caller-owned device
- * memory.  The fp32 vectors are the state_dict tensors as they are (utils.py:29-57 names in
- * the comments); the two weight matrices are pre-split for bf16x3 tensor-core accumulation:
- * hi = bf16(w), lo = bf16(w - hi), each row-major [out, in] like nn.Linear.weight. */
+/* A set of n_probers ImprovedProbe MLPs, packed per prober and kept in caller-owned device memory
+ * (probing_rag_b200/prober.py packs a list of state_dicts; utils.py:29-57 names in the comments).  The input LayerNorm
+ * is folded around fc1 -- fc1(LN(x)) = rstd * (W' x - mean * rowsum(W')) + (W beta + b1) with W' = W diag(gamma) -- so
+ * the tensor cores multiply the raw hidden states and the kernel's epilogue applies the row statistics:
+ *   w1_hi / w1_lo   fc1.weight * layer_norm_input.weight[None, :], split for bf16x3 accumulation
+ *                   (hi = bf16(w), lo = bf16(w - hi), row-major [out, in] like nn.Linear.weight)
+ *   w1_rowsum       its row sums
+ *   b1              fc1.bias + fc1.weight @ layer_norm_input.bias
+ * The other vectors are the state_dict tensors as they are; fc2.weight is split the same way. */
 typedef struct pr_prober_set {
     int32_t n_probers;               /* <= PR_PROBER_MAX; 6 in the reference (exp_rag.py:311) */
     int32_t d_model;                 /* 2048 (gemma-2b); multiple of 128, <= 2048             */
     int32_t hidden;                  /* 512                                                   */
-    const float *ln_in_w, *ln_in_b;  /* [P][d_model]   layer_norm_input.{weight,bias}         */
-    const float *b1;                 /* [P][hidden]    fc1.bias                               */
+    const float *w1_rowsum;          /* [P][hidden]    see above                              */
+    const float *b1;                 /* [P][hidden]    see above                              */
     const float *ln1_w, *ln1_b;      /* [P][hidden]    layer_norm1.{weight,bias}              */
     const float *b2;                 /* [P][hidden]    fc2.bias                               */
     const float *ln2_w, *ln2_b;      /* [P][hidden]    layer_norm2.{weight,bias}              */
     const float *w3, *b3;            /* [P][2][hidden], [P][2]   fc3 (kept fp32)              */
-    const void *w1_hi, *w1_lo;       /* bf16 [P][hidden][d_model]  fc1.weight split, 128-byte aligned */
+    const void *w1_hi, *w1_lo;       /* bf16 [P][hidden][d_model]  see above, 128-byte aligned */
     const void *w2_hi, *w2_lo;       /* bf16 [P][hidden][hidden]   fc2.weight split, 128-byte aligned */
 } pr_prober_set_t;
 

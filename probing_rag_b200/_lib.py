@@ -32,7 +32,7 @@ class AuxInfo(ctypes.Structure):
 
 class ProberSet(ctypes.Structure):
     _fields_ = [("n_probers", c_i32), ("d_model", c_i32), ("hidden", c_i32),
-                ("ln_in_w", c_vp), ("ln_in_b", c_vp), ("b1", c_vp),
+                ("w1_rowsum", c_vp), ("b1", c_vp),
                 ("ln1_w", c_vp), ("ln1_b", c_vp), ("b2", c_vp),
                 ("ln2_w", c_vp), ("ln2_b", c_vp), ("w3", c_vp), ("b3", c_vp),
                 ("w1_hi", c_vp), ("w1_lo", c_vp), ("w2_hi", c_vp), ("w2_lo", c_vp)]

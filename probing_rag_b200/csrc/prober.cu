@@ -13,7 +13,6 @@
 // LayerNorm statistics, SiLU, softmax and fc3 (512->2) stay in fp32 on the CUDA cores.
 //
 // Kernels
-//   prober_ln_split_kernel   x (f32 / bf16 / f16) -> LN_in -> (hi, lo) bf16, one warp per row
 //   prober_gemm_kernel<EPI>  a CTA PAIR (cluster of 2, the two SMs of a TPC) = 256 rows x 512 columns of one prober;
 //                            each CTA owns 128 rows and the whole 128x512 fp32 accumulator of them in its TMEM.
 //        warp 0  TMA producer   per k-block of 64: this CTA's A(hi,lo)[128x64] and HALF of B: for each 256-column
@@ -88,6 +87,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 // shared::cluster address of a barrier of the PAIR'S LEADER (even CTA): the same offset with the peer bit cleared
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
 // TMA load into THIS CTA's shared memory whose completion bytes are counted by the leader CTA's barrier
+// wait with cluster-scope acquire: the phase is completed by arrivals from both CTAs of the pair
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
 __device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
 {
     asm volatile(
@@ -105,6 +120,11 @@ __device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t cols)
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols)
 {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// arrive (release, cluster scope) on the barrier at this offset in the pair's LEADER CTA
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank()
 {
@@ -217,61 +237,6 @@ __device__ __forceinline__ float4 load_x4<__half>(const __half *x, int i)
     return make_float4(a.x, a.y, b.x, b.y);
 }
 
-// Register-light (<= 64 registers, 128 threads per block): the row is not kept in registers between the passes -- the
-// second and third pass re-read it (8 KB per warp, L1/L2 hits; X comes from HBM once).  Same speed as holding the row
-// (HBM-bound either way: 1.6 GB at 16,384 rows x 6), half the registers.
-constexpr int kLnThreads = 128;
-template <typename T>
-__global__ void __launch_bounds__(kLnThreads, 8) prober_ln_split_kernel(const T *__restrict__ X, const float *__restrict__ gamma,
-                                                                       const float *__restrict__ beta, __nv_bfloat16 *__restrict__ a_hi,
-                                                                       __nv_bfloat16 *__restrict__ a_lo, int n_rows, int rows_pad,
-                                                                       int n_probers, int d_model, int p0, int np)
-{
-    const int lane = threadIdx.x & 31;
-    const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (wid >= (int64_t)n_rows * np) return;
-    const int row = (int)(wid / np), p = p0 + (int)(wid % np);   // probers [p0, p0 + np) of every row
-    const T *xrow = X + ((size_t)row * n_probers + p) * d_model;
-    const int nv = d_model >> 7;  // 4-feature groups per lane (16 for d_model = 2048)
-    float sum = 0.f;
-#pragma unroll 4
-    for (int i = 0; i < nv; ++i) {
-        const float4 v = load_x4<T>(xrow, lane + 32 * i);
-        sum += (v.x + v.y) + (v.z + v.w);
-    }
-    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(PR_FULL_MASK, sum, o);
-    const float mean = sum / (float)d_model;
-    float sq = 0.f;
-#pragma unroll 4
-    for (int i = 0; i < nv; ++i) {
-        const float4 v = load_x4<T>(xrow, lane + 32 * i);
-        const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
-        sq += (a * a + b * b) + (c * c + d * d);
-    }
-    for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(PR_FULL_MASK, sq, o);
-    const float rstd = rsqrtf(sq / (float)d_model + kLnEps);
-    const float4 *g4 = reinterpret_cast<const float4 *>(gamma + (size_t)p * d_model);
-    const float4 *b4 = reinterpret_cast<const float4 *>(beta + (size_t)p * d_model);
-    const size_t out_row = ((size_t)p * rows_pad + row) * d_model;
-#pragma unroll 2
-    for (int i = 0; i < nv; ++i) {
-        const float4 v = load_x4<T>(xrow, lane + 32 * i);
-        const float4 g = g4[lane + 32 * i], b = b4[lane + 32 * i];
-        const float y[4] = {(v.x - mean) * rstd * g.x + b.x, (v.y - mean) * rstd * g.y + b.y,
-                            (v.z - mean) * rstd * g.z + b.z, (v.w - mean) * rstd * g.w + b.w};
-        __nv_bfloat16 h[4], l[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) split_bf16(y[k], h[k], l[k]);
-        const size_t o = out_row + (size_t)(lane + 32 * i) * 4;
-        const uint2 hv = make_uint2((uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16),
-                                    (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16));
-        const uint2 lv = make_uint2((uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16),
-                                    (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16));
-        *reinterpret_cast<uint2 *>(a_hi + o) = hv;
-        *reinterpret_cast<uint2 *>(a_lo + o) = lv;
-    }
-}
-
 // ------------------------------------------------------------------ GEMM + fused epilogue
 struct GemmArgs {
     int n_rows, rows_pad, K;
@@ -283,11 +248,25 @@ struct GemmArgs {
     float *probs;                     // [rows][P][2]                 (EPI 2)
     int n_probers;
     int p0;                           // first prober of this launch (blockIdx.y counts from it)
+    // EPI 1: the A operand is produced in the kernel from the pooled hidden states (input LayerNorm fused)
+    const void *X;                    // [rows][P][d_model] of the kernel's XT
+    const float *w1_rowsum;           // [P][512] row sums of fc1.weight * layer_norm_input.weight
 };
 
-constexpr size_t kGemmSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 5 * kHidden * 4 + 256 + 4 * kEpiThreads * 4;
+constexpr size_t kGemmSmemBytes =
+    1024 /*align slack*/ + (size_t)kStages * kStageBytes + 5 * kHidden * 4 + 256 + 4 * kEpiThreads * 4 + 2 * kBM * 4;
 
-template <int EPI>
+// EPI 1 (fc1): the input LayerNorm is folded AROUND the GEMM and the A operand never exists in global memory.
+//     fc1(LN(x)) = rstd * (W' x - mean * rowsum(W')) + (W beta + b1),   W' = W diag(gamma)
+// so the tensor cores multiply the RAW hidden states by W' (packed once per checkpoint, prober.py) and the epilogue
+// applies rstd, the mean term and the shifted bias per row.  The 8 epilogue warps -- idle while the MMAs run -- stream
+// X[128 rows, 64 features] k-block by k-block (each element of X is read from HBM exactly once, one k-block ahead of
+// the MMAs), split it into (hi, lo) bf16 straight into the stage in the 128-byte-swizzled K-major layout the tensor
+// core reads, and accumulate every row's sum and sum of squares (shifted by the row's first feature) on the way: by
+// the time the accumulator is complete so are mean and rstd.  This replaces a separate LayerNorm kernel that read X
+// and wrote + re-read 2 x 403 MB of split operand (0.32 of 1.05 ms at 16,384 rows) and needs no statistics pre-pass.
+// XT = dtype of X (f32 / bf16 / f16).   EPI 2 (fc2) loads A with TMA.
+template <int EPI, typename XT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 prober_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -305,6 +284,8 @@ prober_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     uint64_t *acc_bar = empty_bar + kStages;                                // accumulator complete
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_bar + 1);
     float *s_red = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(full_bar) + 256);  // [4][kEpiThreads] row partials
+    float *s_mean = s_red + 4 * kEpiThreads;                                // [kBM] input LayerNorm statistics (EPI 1)
+    float *s_rstd = s_mean + kBM;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p = g.p0 + blockIdx.y;          // prober
@@ -314,7 +295,9 @@ prober_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(&full_bar[s], 1);       // (used in the leader CTA only: its producer's arrive + both CTAs' bytes)
+            // (used in the leader CTA only) its producer's arrive + both CTAs' TMA bytes; EPI 1: + one arrival per
+            // CTA once its epilogue warps have written their A tiles
+            mbar_init(&full_bar[s], EPI == 1 ? 3 : 1);
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(acc_bar, 1);
@@ -331,6 +314,8 @@ prober_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             if (EPI == 2) {
                 s_w3[i] = g.w3[((size_t)p * 2 + 0) * kHidden + i];
                 s_w3[kHidden + i] = g.w3[((size_t)p * 2 + 1) * kHidden + i];
+            } else {
+                s_w3[i] = g.w1_rowsum[(size_t)p * kHidden + i];   // (EPI 1 has no fc3: the array holds rowsum(W'))
             }
         }
     }
@@ -347,10 +332,12 @@ prober_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             const uint32_t ph = (uint32_t)(it / kStages) & 1u;
             mbar_wait(&empty_bar[s], ph ^ 1u);
             unsigned char *st = stage_base + (size_t)s * kStageBytes;
-            if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * kStageBytes);
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * (EPI == 1 ? 4 : 6) * kTileBytes);
             const int a_row = p * g.rows_pad + row0, b_row = p * kHidden + (int)cta_rank * kBNC;
-            tma_load_2d_pair(st, &map_a_hi, &full_bar[s], it * kBK, a_row);
-            tma_load_2d_pair(st + kTileBytes, &map_a_lo, &full_bar[s], it * kBK, a_row);
+            if (EPI == 2) {
+                tma_load_2d_pair(st, &map_a_hi, &full_bar[s], it * kBK, a_row);
+                tma_load_2d_pair(st + kTileBytes, &map_a_lo, &full_bar[s], it * kBK, a_row);
+            }
             tma_load_2d_pair(st + 2 * kTileBytes, &map_b_hi, &full_bar[s], it * kBK, b_row);
             tma_load_2d_pair(st + 3 * kTileBytes, &map_b_hi, &full_bar[s], it * kBK, b_row + kBNH);
             tma_load_2d_pair(st + 4 * kTileBytes, &map_b_lo, &full_bar[s], it * kBK, b_row);
@@ -361,7 +348,7 @@ prober_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         for (int it = 0; it < n_iter; ++it) {
             const int s = it % kStages;
             const uint32_t ph = (uint32_t)(it / kStages) & 1u;
-            mbar_wait(&full_bar[s], ph);
+            mbar_wait_cluster(&full_bar[s], ph);
             tc_fence_after();
             const uint32_t st = smem_u32(stage_base + (size_t)s * kStageBytes);
             const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kTileBytes);
@@ -384,25 +371,106 @@ prober_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         // ===== epilogue: TMEM lane t = row row0+t is shared by kEpiSplit threads (warps w, w+4, w+8, .. see the same
         // lane quadrant): thread (part, t) owns columns [part * kEpiCols, +kEpiCols) and the row statistics are combined
         // through shared memory (every thread of a row sums the parts in the same order: identical values)
+        const int et = threadIdx.x - 128;
+        auto epi_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); };
+        if (EPI == 1) {
+            // ===== A-operand producer.  Lane l of warp w owns the 4 features [4 (l % 16), +4) of the k-block in the 8
+            // rows w * 16 + 2 i + l / 16 (i = 0..7): every load instruction of a warp covers two whole 256-byte row
+            // segments of X (coalesced), and the k-block after the current one is already in registers while the
+            // barrier of the current stage is awaited.  (A first version -- one thread per half row, no look-ahead,
+            // the row normalised here after a statistics pre-pass -- made fc1 1.8x slower than the unfused kernel.)  Tile layout (what TMA's SWIZZLE_128B writes): row r at byte
+            // r * 128, its 16-byte chunk j stored at chunk position j ^ (r % 8).
+            const int c4 = lane & 15, rsub = lane >> 4, rbase = (warp - 4) * (kBM / (kEpiThreads / 32));
+            constexpr int kRowsPerThread = kBM / (kEpiThreads / 32) / 2;   // 8
+            const XT *xrow[kRowsPerThread];
+            uint32_t dst[kRowsPerThread];   // byte offset of this thread's 8 bytes inside an A tile
+            float shift[kRowsPerThread], sum[kRowsPerThread], sq[kRowsPerThread];
+            float4 cur[kRowsPerThread], nxt[kRowsPerThread];
+#pragma unroll
+            for (int i = 0; i < kRowsPerThread; ++i) {
+                const int r = rbase + 2 * i + rsub;
+                const bool live = row0 + r < g.n_rows;   // (padding rows read row 0: their results are never stored)
+                xrow[i] = reinterpret_cast<const XT *>(g.X) + ((size_t)(live ? row0 + r : 0) * g.n_probers + p) * g.K;
+                dst[i] = (uint32_t)(r * 128 + (((c4 >> 1) ^ (r & 7)) << 4) + ((c4 & 1) << 3));
+                cur[i] = load_x4<XT>(xrow[i], c4);
+                // statistics are accumulated around the row's first feature: no E[x^2] - mean^2 cancellation for rows
+                // with a large common offset
+                shift[i] = __shfl_sync(PR_FULL_MASK, cur[i].x, lane & 16);
+                sum[i] = 0.f;
+                sq[i] = 0.f;
+            }
+            for (int it = 0; it < n_iter; ++it) {
+                const int s = it % kStages;
+                const uint32_t ph = (uint32_t)(it / kStages) & 1u;
+                if (it + 1 < n_iter) {
+                    const int qn = (it + 1) * (kBK / 4) + c4;   // this thread's 4-feature group in the next k-block
+#pragma unroll
+                    for (int i = 0; i < kRowsPerThread; ++i) nxt[i] = load_x4<XT>(xrow[i], qn);
+                }
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                unsigned char *a_hi_t = stage_base + (size_t)s * kStageBytes, *a_lo_t = a_hi_t + kTileBytes;
+#pragma unroll
+                for (int i = 0; i < kRowsPerThread; ++i) {
+                    const float x[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
+                    __nv_bfloat16 hh[4], ll[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        split_bf16(x[k], hh[k], ll[k]);
+                        const float d = x[k] - shift[i];
+                        sum[i] += d;
+                        sq[i] = fmaf(d, d, sq[i]);
+                    }
+                    *reinterpret_cast<uint2 *>(a_hi_t + dst[i]) =
+                        make_uint2((uint32_t)__bfloat16_as_ushort(hh[0]) | ((uint32_t)__bfloat16_as_ushort(hh[1]) << 16),
+                                   (uint32_t)__bfloat16_as_ushort(hh[2]) | ((uint32_t)__bfloat16_as_ushort(hh[3]) << 16));
+                    *reinterpret_cast<uint2 *>(a_lo_t + dst[i]) =
+                        make_uint2((uint32_t)__bfloat16_as_ushort(ll[0]) | ((uint32_t)__bfloat16_as_ushort(ll[1]) << 16),
+                                   (uint32_t)__bfloat16_as_ushort(ll[2]) | ((uint32_t)__bfloat16_as_ushort(ll[3]) << 16));
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
+                epi_sync();
+                if (et == 0) mbar_arrive_leader(&full_bar[s]);
+#pragma unroll
+                for (int i = 0; i < kRowsPerThread; ++i) cur[i] = nxt[i];
+            }
+            // row statistics: the 16 lanes that share a row add up their parts
+#pragma unroll
+            for (int i = 0; i < kRowsPerThread; ++i) {
+                float a = sum[i], b = sq[i];
+#pragma unroll
+                for (int o = 8; o; o >>= 1) {
+                    a += __shfl_xor_sync(PR_FULL_MASK, a, o);
+                    b += __shfl_xor_sync(PR_FULL_MASK, b, o);
+                }
+                if (c4 == 0) {
+                    const float inv_k = 1.f / (float)g.K, m = a * inv_k;
+                    s_mean[rbase + 2 * i + rsub] = shift[i] + m;
+                    s_rstd[rbase + 2 * i + rsub] = rsqrtf(fmaxf(b * inv_k - m * m, 0.f) + kLnEps);   // biased variance
+                }
+            }
+            epi_sync();
+        }
         mbar_wait(acc_bar, 0);
         tc_fence_after();
-        const int et = threadIdx.x - 128;
         const int part = et >> 7, t = et & 127;
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         const int row = row0 + t;
         const int cb = part * kEpiCols, ce = cb + kEpiCols;
-        auto epi_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); };
         uint32_t r[32];
         // pass 1: bias + SiLU, keep the activations in TMEM; row mean and centred second moment in the same pass:
         // exact two-pass statistics of every 32-column chunk while it sits in registers, chunks (and then the parts
         // of the row) merged with Chan's formula -- no second sweep over TMEM, no E[x^2] - mean^2 cancellation
         float run_mean = 0.f, run_m2 = 0.f;
+        const float in_rstd = EPI == 1 ? s_rstd[t] : 1.f, in_mean_rstd = EPI == 1 ? s_mean[t] * s_rstd[t] : 0.f;
         for (int c0 = cb; c0 < ce; c0 += 32) {
             tmem_ld32(taddr + c0, r);
             float csum = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const float a = silu(__uint_as_float(r[j]) + s_bias[c0 + j]);
+                // EPI 1: fc1(LN(x))_j = rstd * acc_j - (mean * rstd) * rowsum(W')_j + (W beta + b1)_j
+                const float pre = EPI == 1 ? fmaf(__uint_as_float(r[j]), in_rstd, fmaf(-in_mean_rstd, s_w3[c0 + j], s_bias[c0 + j]))
+                                           : __uint_as_float(r[j]) + s_bias[c0 + j];
+                const float a = silu(pre);
                 csum += a;
                 r[j] = __float_as_uint(a);
             }
@@ -525,32 +593,41 @@ __global__ void prober_gate_kernel(const float *__restrict__ probs, int n_rows, 
     if (threadIdx.x == 0) block_cnt[blockIdx.x] = c;
 }
 
-__global__ void prober_scan_kernel(int32_t *block_cnt, int n_blocks, int32_t *n_retrieve)
-{
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        int acc = 0;
-        for (int i = 0; i < n_blocks; ++i) {
-            const int v = block_cnt[i];
-            block_cnt[i] = acc;
-            acc += v;
-        }
-        *n_retrieve = acc;
-    }
-}
-
-__global__ void prober_compact_kernel(const uint8_t *__restrict__ mask, int n_rows, const int32_t *__restrict__ block_off,
-                                      int32_t *__restrict__ compact)
+// Ordered compaction of the rows that retrieve.  Every block adds up the counts of the blocks before it itself (a few
+// dozen values: no scan kernel), block 0 publishes the total, and the thread of row i also writes the -1 that fills
+// slot i when i lies past the total (no memset in front).
+__global__ void prober_compact_kernel(const uint8_t *__restrict__ mask, int n_rows, const int32_t *__restrict__ block_cnt,
+                                      int32_t *__restrict__ compact, int32_t *__restrict__ n_retrieve)
 {
     __shared__ int warp_cnt[32];
+    __shared__ int s_before, s_total;
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int flag = row < n_rows && mask[row];
     const unsigned m = __ballot_sync(PR_FULL_MASK, flag);
     if (lane == 0) warp_cnt[w] = __popc(m);
+    if (w == 0) {
+        int before = 0, total = 0;
+        for (int i = lane; i < (int)gridDim.x; i += 32) {
+            const int c = block_cnt[i];
+            total += c;
+            if (i < (int)blockIdx.x) before += c;
+        }
+        for (int o = 16; o; o >>= 1) {
+            before += __shfl_xor_sync(PR_FULL_MASK, before, o);
+            total += __shfl_xor_sync(PR_FULL_MASK, total, o);
+        }
+        if (lane == 0) {
+            s_before = before;
+            s_total = total;
+            if (blockIdx.x == 0) *n_retrieve = total;
+        }
+    }
     __syncthreads();
-    int before = block_off[blockIdx.x];
+    int before = s_before;
     for (int i = 0; i < w; ++i) before += warp_cnt[i];
     if (flag) compact[before + __popc(m & ((1u << lane) - 1u))] = row;
+    if (row < n_rows && row >= s_total) compact[row] = -1;
 }
 
 // ------------------------------------------------------------------------------------ host
@@ -597,7 +674,7 @@ inline size_t up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct ProberLayout {
     int rows_pad;
-    size_t a1_hi, a1_lo, a2_hi, a2_lo, probs, block_cnt, total;
+    size_t a2_hi, a2_lo, probs, block_cnt, total;
 };
 
 ProberLayout prober_layout(int P, int n_rows, int d_model, int hidden)
@@ -605,8 +682,6 @@ ProberLayout prober_layout(int P, int n_rows, int d_model, int hidden)
     ProberLayout l;
     l.rows_pad = (n_rows + 2 * kBM - 1) / (2 * kBM) * (2 * kBM);   // whole CTA pairs
     size_t o = 0;
-    l.a1_hi = o; o = up(o + (size_t)P * l.rows_pad * d_model * 2, 1024);
-    l.a1_lo = o; o = up(o + (size_t)P * l.rows_pad * d_model * 2, 1024);
     l.a2_hi = o; o = up(o + (size_t)P * l.rows_pad * hidden * 2, 1024);
     l.a2_lo = o; o = up(o + (size_t)P * l.rows_pad * hidden * 2, 1024);
     l.probs = o; o = up(o + (size_t)n_rows * P * 2 * 4, 256);
@@ -669,15 +744,12 @@ extern "C" int pr_prober_forward(const pr_prober_set_t *ps, int32_t n_rows, cons
         return PR_OK;
     }
     unsigned char *ws = (unsigned char *)workspace_dev;
-    __nv_bfloat16 *a1_hi = (__nv_bfloat16 *)(ws + l.a1_hi), *a1_lo = (__nv_bfloat16 *)(ws + l.a1_lo);
     __nv_bfloat16 *a2_hi = (__nv_bfloat16 *)(ws + l.a2_hi), *a2_lo = (__nv_bfloat16 *)(ws + l.a2_lo);
     float *probs = (float *)(ws + l.probs);
     int32_t *block_cnt = (int32_t *)(ws + l.block_cnt);
 
-    CUtensorMap m_a1h, m_a1l, m_w1h, m_w1l, m_a2h, m_a2l, m_w2h, m_w2l;
+    CUtensorMap m_w1h, m_w1l, m_a2h, m_a2l, m_w2h, m_w2l;
     int rc;
-    if ((rc = make_map(&m_a1h, a1_hi, (uint64_t)P * l.rows_pad, ps->d_model, kBM)) != PR_OK) return rc;
-    if ((rc = make_map(&m_a1l, a1_lo, (uint64_t)P * l.rows_pad, ps->d_model, kBM)) != PR_OK) return rc;
     if ((rc = make_map(&m_w1h, ps->w1_hi, (uint64_t)P * kHidden, ps->d_model, kBNC)) != PR_OK) return rc;
     if ((rc = make_map(&m_w1l, ps->w1_lo, (uint64_t)P * kHidden, ps->d_model, kBNC)) != PR_OK) return rc;
     if ((rc = make_map(&m_a2h, a2_hi, (uint64_t)P * l.rows_pad, kHidden, kBM)) != PR_OK) return rc;
@@ -685,68 +757,51 @@ extern "C" int pr_prober_forward(const pr_prober_set_t *ps, int32_t n_rows, cons
     if ((rc = make_map(&m_w2h, ps->w2_hi, (uint64_t)P * kHidden, kHidden, kBNC)) != PR_OK) return rc;
     if ((rc = make_map(&m_w2l, ps->w2_lo, (uint64_t)P * kHidden, kHidden, kBNC)) != PR_OK) return rc;
 
-    static bool attr_done = false;  // (idempotent; a race only repeats the call)
-    if (!attr_done) {
-        PR_CUDA_CHECK(cudaFuncSetAttribute(prober_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
-        PR_CUDA_CHECK(cudaFuncSetAttribute(prober_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
-        attr_done = true;
+    typedef void (*gemm_fn_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmArgs);
+    const gemm_fn_t fc1 = x_dtype == 0 ? prober_gemm_kernel<1, float>
+                          : x_dtype == 1 ? prober_gemm_kernel<1, __nv_bfloat16> : prober_gemm_kernel<1, __half>;
+    const gemm_fn_t fc2 = prober_gemm_kernel<2, float>;
+    static bool attr_done[4] = {false, false, false, false};  // (idempotent; a race only repeats the call)
+    if (!attr_done[x_dtype]) {
+        PR_CUDA_CHECK(cudaFuncSetAttribute((const void *)fc1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
+        attr_done[x_dtype] = true;
+    }
+    if (!attr_done[3]) {
+        PR_CUDA_CHECK(cudaFuncSetAttribute((const void *)fc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
+        attr_done[3] = true;
     }
     GemmArgs g;
     g.n_rows = n_rows;
     g.rows_pad = l.rows_pad;
     g.n_probers = P;
+    g.p0 = 0;
     g.w3 = ps->w3;
     g.b3 = ps->b3;
     g.out_hi = a2_hi;
     g.out_lo = a2_lo;
     g.logits = out_logits_dev;
     g.probs = probs;
-
-    auto launch_ln = [&](cudaStream_t s, int p0, int np) -> int {
-        const int64_t warps = (int64_t)n_rows * np;
-        const unsigned nb = (unsigned)((warps + kLnThreads / 32 - 1) / (kLnThreads / 32));
-        if (x_dtype == 0)
-            prober_ln_split_kernel<float><<<nb, kLnThreads, 0, s>>>((const float *)X_dev, ps->ln_in_w, ps->ln_in_b, a1_hi, a1_lo, n_rows,
-                                                             l.rows_pad, P, ps->d_model, p0, np);
-        else if (x_dtype == 1)
-            prober_ln_split_kernel<__nv_bfloat16><<<nb, kLnThreads, 0, s>>>((const __nv_bfloat16 *)X_dev, ps->ln_in_w, ps->ln_in_b, a1_hi,
-                                                                     a1_lo, n_rows, l.rows_pad, P, ps->d_model, p0, np);
-        else
-            prober_ln_split_kernel<__half><<<nb, kLnThreads, 0, s>>>((const __half *)X_dev, ps->ln_in_w, ps->ln_in_b, a1_hi, a1_lo, n_rows,
-                                                              l.rows_pad, P, ps->d_model, p0, np);
-        PR_CUDA_CHECK(cudaGetLastError());
-        return PR_OK;
-    };
-    auto launch_gemms = [&](int p0, int np) -> int {
-        const dim3 grid((unsigned)(l.rows_pad / kBM), (unsigned)np);
-        g.p0 = p0;
-        // fc1 + SiLU + LN1 -> split operand of fc2
-        g.K = ps->d_model;
-        g.bias = ps->b1;
-        g.ln_w = ps->ln1_w;
-        g.ln_b = ps->ln1_b;
-        prober_gemm_kernel<1><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(m_a1h, m_a1l, m_w1h, m_w1l, g);
-        // fc2 + SiLU + LN2 + fc3 + softmax
-        g.K = kHidden;
-        g.bias = ps->b2;
-        g.ln_w = ps->ln2_w;
-        g.ln_b = ps->ln2_b;
-        prober_gemm_kernel<2><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(m_a2h, m_a2l, m_w2h, m_w2l, g);
-        PR_CUDA_CHECK(cudaGetLastError());
-        return PR_OK;
-    };
-
-    // LN of all probers, then both GEMMs over all probers, on the caller's stream.  (Measured and dropped: running the
-    // HBM-bound input LayerNorm of prober p+1 on a side stream while the GEMMs of prober p run -- no gain at 16,384
-    // rows, the GEMMs slow down by what the overlap saves, and per-prober launches cost mid-size batches 4x.)
-    if ((rc = launch_ln(st, 0, P)) != PR_OK) return rc;
-    if ((rc = launch_gemms(0, P)) != PR_OK) return rc;
+    g.X = X_dev;
+    g.w1_rowsum = ps->w1_rowsum;
+    const dim3 grid((unsigned)(l.rows_pad / kBM), (unsigned)P);
+    // kernel 1: input LayerNorm (folded around the GEMM) + fc1 + SiLU + LN1 -> split operand of fc2
+    g.K = ps->d_model;
+    g.bias = ps->b1;
+    g.ln_w = ps->ln1_w;
+    g.ln_b = ps->ln1_b;
+    fc1<<<grid, kGemmThreads, kGemmSmemBytes, st>>>(m_w1h, m_w1l, m_w1h, m_w1l, g);   // (the A maps are unused by EPI 1)
+    PR_CUDA_CHECK(cudaGetLastError());
+    // kernel 2: fc2 + SiLU + LN2 + fc3 + softmax
+    g.K = kHidden;
+    g.bias = ps->b2;
+    g.ln_w = ps->ln2_w;
+    g.ln_b = ps->ln2_b;
+    fc2<<<grid, kGemmThreads, kGemmSmemBytes, st>>>(m_a2h, m_a2l, m_w2h, m_w2l, g);
+    PR_CUDA_CHECK(cudaGetLastError());
     // gate + ordered compaction of the rows that retrieve
     const int nb = (n_rows + 255) / 256;
-    PR_CUDA_CHECK(cudaMemsetAsync(out_compact_idx_dev, 0xff, (size_t)n_rows * 4, st));  // entries past n_retrieve read -1
     prober_gate_kernel<<<nb, 256, 0, st>>>(probs, n_rows, P, theta, ablation, out_probsum_dev, out_retrieve_mask_dev, block_cnt);
-    prober_scan_kernel<<<1, 32, 0, st>>>(block_cnt, nb, out_n_retrieve_dev);
-    prober_compact_kernel<<<nb, 256, 0, st>>>(out_retrieve_mask_dev, n_rows, block_cnt, out_compact_idx_dev);
+    prober_compact_kernel<<<nb, 256, 0, st>>>(out_retrieve_mask_dev, n_rows, block_cnt, out_compact_idx_dev, out_n_retrieve_dev);
     PR_CUDA_CHECK(cudaGetLastError());
     return PR_OK;
 }

@@ -105,13 +105,20 @@ class ProberGate:
             return torch.stack([sd[key].detach().to(dev, torch.float32) for sd in sds]).contiguous()
 
         self.t = {k: stack(k) for k in STATE_KEYS if k not in ("fc1.weight", "fc2.weight")}
-        self.w1_hi, self.w1_lo = split_bf16(stack("fc1.weight"))
+        # The input LayerNorm is folded around fc1 (include/probing_rag.h): fc1(LN(x)) = rstd * (W' x - mean * rowsum(W'))
+        # + (W beta + b1) with W' = W diag(gamma).  Folded once per checkpoint, in float64, rounded to f32 once.
+        w1 = stack("fc1.weight").double()
+        gamma, beta = self.t["layer_norm_input.weight"].double(), self.t["layer_norm_input.bias"].double()
+        w1g = (w1 * gamma[:, None, :]).float()
+        self.w1_hi, self.w1_lo = split_bf16(w1g)
+        # row sums of exactly what the tensor cores multiply by (hi + lo), so the mean term cancels what they add
+        self.w1_rowsum = (self.w1_hi.double() + self.w1_lo.double()).sum(-1).float().contiguous()
+        self.b1_folded = (torch.einsum("pod,pd->po", w1, beta) + self.t["fc1.bias"].double()).float().contiguous()
         self.w2_hi, self.w2_lo = split_bf16(stack("fc2.weight"))
         t = self.t
         self._set = _lib.ProberSet(
             n_probers=self.n_probers, d_model=self.d_model, hidden=self.hidden,
-            ln_in_w=t["layer_norm_input.weight"].data_ptr(), ln_in_b=t["layer_norm_input.bias"].data_ptr(),
-            b1=t["fc1.bias"].data_ptr(), ln1_w=t["layer_norm1.weight"].data_ptr(), ln1_b=t["layer_norm1.bias"].data_ptr(),
+            w1_rowsum=self.w1_rowsum.data_ptr(), b1=self.b1_folded.data_ptr(), ln1_w=t["layer_norm1.weight"].data_ptr(), ln1_b=t["layer_norm1.bias"].data_ptr(),
             b2=t["fc2.bias"].data_ptr(), ln2_w=t["layer_norm2.weight"].data_ptr(), ln2_b=t["layer_norm2.bias"].data_ptr(),
             w3=t["fc3.weight"].data_ptr(), b3=t["fc3.bias"].data_ptr(),
             w1_hi=self.w1_hi.data_ptr(), w1_lo=self.w1_lo.data_ptr(),

@@ -47,11 +47,11 @@ constexpr int kTileBytes = kBM * kBK * 2;      // every operand tile is 128 rows
 constexpr int kStageBytes = 6 * kTileBytes;    // 96 KB
 static_assert(kBNC == kBM, "operand tiles share one box shape");
 #ifndef PR_EPI_SPLIT
-#define PR_EPI_SPLIT 2
+#define PR_EPI_SPLIT 4
 #endif
-// Epilogue threads per row, each owning kHidden / kEpiSplit columns.  4 (16 warps, 96 registers) was measured equal to
-// 2 (8 warps, 120 / 168 registers) at 16,384 rows: the shorter epilogue is paid back by the input-LayerNorm blocks of
-// the next prober no longer fitting beside the GEMM CTA (profiles/r02/prober_history.md).
+// Epilogue threads per row, each owning kHidden / kEpiSplit columns.  The epilogue (tcgen05.ld -> SFU -> tcgen05.st
+// chains) and the A-operand producer of fc1 are latency-bound: 4 (16 warps, 96 registers) measured 0.77 ms per
+// 16,384 x 6 against 0.80 ms with 2 (8 warps).
 constexpr int kEpiSplit = PR_EPI_SPLIT;
 constexpr int kEpiThreads = 128 * kEpiSplit;
 constexpr int kGemmThreads = 128 + kEpiThreads;    // warps 0-2: TMA / MMA / TMEM alloc, warp 3 idle, then the epilogue

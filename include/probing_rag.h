@@ -51,6 +51,11 @@ typedef struct pr_bm25_tuning {
                                 small batch is ONE scoring launch + one merge */
     int32_t items_per_warp;  /* small batches: work items per resident warp the plan aims for (default 1:
                                 per-item set-up dominates a single query, measured in profiles/r02) */
+    int32_t tile_epochs;     /* large batches: 4 (default) = the score tile is re-zeroed every 4th sub-tile (needs every
+                                weight in [2^-30, 2^8], else 2 is used), 2 = every 2nd (A/B and tests) */
+    int32_t batch_variant;   /* which variant of the scoring kernel runs: 3 (default) = by batch size (batches smaller
+                                than twice the resident warps take the small-batch variant, whose warps re-read a query's
+                                bound in front of tile scans), 1 = always the small-batch, 2 = always the large-batch variant */
 } pr_bm25_tuning_t;
 
 int pr_version(void);

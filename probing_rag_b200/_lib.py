@@ -21,7 +21,8 @@ c_i32, c_i64, c_f32, c_vp, c_sz = ctypes.c_int32, ctypes.c_int64, ctypes.c_float
 
 class Tuning(ctypes.Structure):
     _fields_ = [("subs_per_item", c_i32), ("warps_per_cta", c_i32), ("docs_per_launch", c_i32),
-                ("min_items", c_i32), ("items_per_warp", c_i32)]
+                ("min_items", c_i32), ("items_per_warp", c_i32), ("tile_epochs", c_i32),
+                ("batch_variant", c_i32)]
 
 
 class AuxInfo(ctypes.Structure):

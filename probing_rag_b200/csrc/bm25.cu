@@ -235,11 +235,16 @@ __global__ void bm25_validate_kernel(const int64_t *indptr, const int32_t *doc_i
         if (b > e || b < 0 || e > nnz) atomicOr(bad, 1);
     }
     if (i0 == 0 && (indptr[0] != 0 || indptr[n_terms] != nnz)) atomicOr(bad, 1);
+    uint32_t wmin = 0xffffffffu, wmax = 0u;   // non-negative floats order like their bit patterns
     for (int64_t p = i0; p < nnz; p += stride) {
         const int32_t d = doc_ids[p];
         const float w = weights[p];
         if (d < 0 || d >= n_docs) atomicOr(bad, 2);
         if (!(w >= 0.f) || w > 3.0e38f) atomicOr(bad, 8);
+        else {
+            wmin = min(wmin, __float_as_uint(w));
+            wmax = max(wmax, __float_as_uint(w));
+        }
         if (p > 0 && d <= doc_ids[p - 1]) {
             // a descent is only legal where a new term's list starts: p must be in indptr
             int64_t lo = 0, hi = n_terms;
@@ -250,6 +255,14 @@ __global__ void bm25_validate_kernel(const int64_t *indptr, const int32_t *doc_i
             }
             if (indptr[lo] != p) atomicOr(bad, 4);
         }
+    }
+    for (int o = 16; o; o >>= 1) {
+        wmin = min(wmin, __shfl_xor_sync(PR_FULL_MASK, wmin, o));
+        wmax = max(wmax, __shfl_xor_sync(PR_FULL_MASK, wmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(reinterpret_cast<uint32_t *>(bad) + 1, wmin);
+        atomicMax(reinterpret_cast<uint32_t *>(bad) + 2, wmax);
     }
 }
 
@@ -289,7 +302,9 @@ struct pr_index {
     uint32_t hot_base_g;
     // per-kernel launch configuration, resolved once (cudaFuncSetAttribute + occupancy query are host latency that a
     // single-query call would pay every time): occupancy by (warps-per-CTA choice, E choice), 0 = not resolved yet
-    int occ[kNwChoices][kEChoices][2];
+    int occ[kNwChoices][kEChoices][3];
+    float max_weight;  // largest weight of the index
+    bool scale_ok;     // weights in [2^-30, 2^8]: large batches use the four-epoch kernel variant
     // thresholds shared with the other GPUs of a doc-sharded corpus (pr_index_set_peer_thetas): our array of
     // 2 x peer_capacity floats (one half per call parity), the device table of the peers' arrays, the call counter
     float *peer_local;
@@ -409,12 +424,14 @@ void default_tuning(pr_bm25_tuning_t *t)
     t->docs_per_launch = 393216;
     t->min_items = 32768;
     t->items_per_warp = 1;
+    t->tile_epochs = 4;
+    t->batch_variant = 3;
 }
 
 int check_tuning(const pr_bm25_tuning_t &t)
 {
     if (t.subs_per_item < 1 || t.docs_per_launch < 1 || t.min_items < 1 || t.items_per_warp < 1 ||
-        (t.warps_per_cta != 4 && t.warps_per_cta != 8 && t.warps_per_cta != 12)) {
+        (t.tile_epochs != 2 && t.tile_epochs != 4) || t.batch_variant < 1 || t.batch_variant > 3 || (t.warps_per_cta != 4 && t.warps_per_cta != 8 && t.warps_per_cta != 12)) {
         pr_set_error("bad tuning (subs_per_item=%d docs_per_launch=%d min_items=%d items_per_warp=%d warps_per_cta=%d; "
                      "warps_per_cta is 4, 8 or 12)",
                      t.subs_per_item, t.docs_per_launch, t.min_items, t.items_per_warp, t.warps_per_cta);
@@ -450,16 +467,17 @@ extern "C" int pr_index_create(pr_index_t **out, int device, int64_t n_docs_glob
     }
     PR_CUDA_CHECK(cudaSetDevice(device));
     int32_t *bad = nullptr;
-    int32_t h_bad = 0;
+    int32_t h_bad3[3] = {0, -1, 0};  // flags, smallest weight (bits, starts at 0xffffffff), largest weight (bits)
     // one-time validation scratch; freed before returning (not on the query path)
-    PR_CUDA_CHECK(cudaMalloc(&bad, 4));
-    cudaError_t e = cudaMemcpy(bad, &h_bad, 4, cudaMemcpyHostToDevice);
+    PR_CUDA_CHECK(cudaMalloc(&bad, 12));
+    cudaError_t e = cudaMemcpy(bad, h_bad3, 12, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
         bm25_validate_kernel<<<1184, 256>>>(indptr_dev, doc_ids_dev, weights_dev, n_terms, nnz, n_docs, bad);
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaMemcpy(&h_bad, bad, 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(h_bad3, bad, 12, cudaMemcpyDeviceToHost);
     cudaFree(bad);
+    const int32_t h_bad = h_bad3[0];
     if (e != cudaSuccess) {
         pr_set_error("pr_index_create: validation failed to run: %s", cudaGetErrorString(e));
         return PR_ECUDA;
@@ -502,6 +520,15 @@ extern "C" int pr_index_create(pr_index_t **out, int device, int64_t n_docs_glob
     ix->hot_stream_bytes = 0;
     ix->cold_stream = nullptr;
     ix->hot_base_g = 0;
+    {   // four tile epochs (bm25_lean.cuh, kernel variant 2) need every weight in [2^-30, 2^8]
+        float wmin = 0.f, wmax = 0.f;
+        if (nnz > 0) {
+            memcpy(&wmin, &h_bad3[1], 4);
+            memcpy(&wmax, &h_bad3[2], 4);
+        }
+        ix->max_weight = wmax;
+        ix->scale_ok = nnz > 0 && wmin >= 9.313225746154785e-10f && wmax <= 256.f;
+    }
     default_tuning(&ix->tuning);
     cudaDeviceProp prop;
     PR_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
@@ -730,6 +757,8 @@ extern "C" int pr_index_set_tuning(pr_index_t *index, const pr_bm25_tuning_t *tu
     if (tuning->docs_per_launch) t.docs_per_launch = tuning->docs_per_launch;
     if (tuning->min_items) t.min_items = tuning->min_items;
     if (tuning->items_per_warp) t.items_per_warp = tuning->items_per_warp;
+    if (tuning->tile_epochs) t.tile_epochs = tuning->tile_epochs;
+    if (tuning->batch_variant) t.batch_variant = tuning->batch_variant;
     const int rc = check_tuning(t);
     if (rc != PR_OK) return rc;
     index->tuning = t;
@@ -854,9 +883,10 @@ extern "C" int pr_bm25_topk_range(pr_index_t *index, int32_t n_queries, const in
     const size_t smem = prl::lean_smem_bytes(nw);
     // items of one query run side by side when the batch is smaller than the resident warps: those warps re-read the
     // query's bound in front of tile scans (REFRESH variant of the kernel)
-    const bool refresh = (int64_t)n_queries < 2 * (int64_t)index->num_sms * kNominalWarpsPerSm;
-    const score_fn_t fn = pick_lean_fn(nw, E, refresh);
-    int &occ = index->occ[nw_idx(nw)][e_idx(E)][refresh ? 1 : 0];
+    const bool refresh = t.batch_variant == 1 || (t.batch_variant != 2 && (int64_t)n_queries < 2 * (int64_t)index->num_sms * kNominalWarpsPerSm);
+    const int var = refresh ? 1 : (index->scale_ok && t.tile_epochs != 2 ? 2 : 0);
+    const score_fn_t fn = pick_lean_fn(nw, E, var);
+    int &occ = index->occ[nw_idx(nw)][e_idx(E)][var];
     if (occ == 0) {
         PR_CUDA_CHECK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PR_CUDA_CHECK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -895,6 +925,7 @@ extern "C" int pr_bm25_topk_range(pr_index_t *index, int32_t n_queries, const in
     w.K = k;
     w.n_sub = index->n_sub;
     w.subs_per_item = l.G;
+    w.max_weight = index->max_weight;
 
     for (int li = launch_begin; li < launch_end; ++li) {
         const int chunk0 = l.launch_chunk0[li], Cl = l.launch_chunks[li];

@@ -8,10 +8,11 @@ namespace prk {
 
 typedef void (*score_fn_t)(const prw::ScoreArgs);
 
-// nw = warps per CTA (4, 8, 12), E = ceil(k / 32) rounded up to 1, 2, 4, refresh = small-batch variant (bm25_lean.cuh)
-score_fn_t pick_lean_fn(int nw, int E, bool refresh);
-score_fn_t pick_lean_fn_nw4(int E, bool refresh);
-score_fn_t pick_lean_fn_nw8(int E, bool refresh);
-score_fn_t pick_lean_fn_nw12(int E, bool refresh);
+// nw = warps per CTA (4, 8, 12), E = ceil(k / 32) rounded up to 1, 2, 4, var = kernel variant (bm25_lean.cuh: 0 large
+// batches / two tile epochs, 1 small batches, 2 large batches / four tile epochs)
+score_fn_t pick_lean_fn(int nw, int E, int var);
+score_fn_t pick_lean_fn_nw4(int E, int var);
+score_fn_t pick_lean_fn_nw8(int E, int var);
+score_fn_t pick_lean_fn_nw12(int E, int var);
 
 }  // namespace prk

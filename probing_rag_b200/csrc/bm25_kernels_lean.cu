@@ -3,11 +3,11 @@
 
 namespace prk {
 
-score_fn_t pick_lean_fn(int nw, int E, bool refresh)
+score_fn_t pick_lean_fn(int nw, int E, int var)
 {
-    if (nw == 4) return pick_lean_fn_nw4(E, refresh);
-    if (nw == 12) return pick_lean_fn_nw12(E, refresh);
-    return pick_lean_fn_nw8(E, refresh);
+    if (nw == 4) return pick_lean_fn_nw4(E, var);
+    if (nw == 12) return pick_lean_fn_nw12(E, var);
+    return pick_lean_fn_nw8(E, var);
 }
 
 }  // namespace prk

@@ -4,14 +4,14 @@
 
 namespace prk {
 
-template <bool R>
+template <int VAR>
 static score_fn_t pick(int E)
 {
-    if (E == 1) return prl::bm25_lean_kernel<8, 1, R>;
-    if (E == 2) return prl::bm25_lean_kernel<8, 2, R>;
-    return prl::bm25_lean_kernel<8, 4, R>;
+    if (E == 1) return prl::bm25_lean_kernel<8, 1, VAR>;
+    if (E == 2) return prl::bm25_lean_kernel<8, 2, VAR>;
+    return prl::bm25_lean_kernel<8, 4, VAR>;
 }
 
-score_fn_t pick_lean_fn_nw8(int E, bool refresh) { return refresh ? pick<true>(E) : pick<false>(E); }
+score_fn_t pick_lean_fn_nw8(int E, int var) { return var == 1 ? pick<1>(E) : var == 2 ? pick<2>(E) : pick<0>(E); }
 
 }  // namespace prk

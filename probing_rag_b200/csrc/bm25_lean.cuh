@@ -149,13 +149,25 @@ static __global__ void __launch_bounds__(256) cold_fill_kernel(const int32_t *__
         cold[p] = make_uint2((uint32_t)(doc_ids[p] & (kSub - 1)) * 4u, __float_as_uint(weights[p]));
 }
 
-// REFRESH: re-read theta[q] in front of tile scans (batches smaller than the resident warps, see end_subtile).  A
-// template parameter, not a run-time flag: with the flag ptxas put a YIELD into the step loop (-2% queries/s;
+// VAR selects the kernel variant:
+//   0  large batches, two tile epochs (sign)                -- any weights; also the first launches of a call, where
+//      bounds are still weak and most sub-tiles are scanned
+//   1  small batches (REFRESH: re-read theta[q] in front of tile scans, see end_subtile), two epochs
+//   2  large batches, four tile epochs (sign x 2^80 scale)  -- indexes whose weights lie in [2^-30, 2^8] (every real
+//      BM25 index): the tile is re-zeroed every FOURTH sub-tile
+// A template parameter, not a run-time flag: with a flag ptxas put a YIELD into the step loop (-2% queries/s;
 // tests/test_capi.py checks the built kernels for it).
-template <int NW, int E, bool REFRESH>
+constexpr float kEpochScale = 1.2089258196146292e+24f;    // 2^80
+constexpr float kEpochUnscale = 8.271806125530277e-25f;   // 2^-80
+constexpr float kEpochCut = 8.881784197001252e-16f;       // 2^-50: above every unscaled stale word, below every weight
+constexpr float kEpochMaxSum = 16777216.f;                // 2^24: four epochs only for queries whose scores stay below
+
+template <int NW, int E, int VAR>
 __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8 ? PR_LEAN_CTAS : NW <= 12 ? 2 : 1))
     bm25_lean_kernel(const ScoreArgs a)
 {
+    constexpr bool REFRESH = VAR == 1;
+    constexpr int kEpochs = VAR == 2 ? 4 : 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -621,10 +633,15 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
         };
 
         StepBuf buf[kPipe];
-        // ring position of the next step to process; bit 30 = sign epoch of the tile (see rmw below: set = the tile holds
-        // the previous sub-tile's sums) -- slot() masks the high bits away, and the flag costs no register of its own
+        // ring position of the next step to process; bits 30..29 = epoch of the tile (see rmw below: non-zero = the tile
+        // still holds sums of earlier sub-tiles) -- slot() masks the high bits away, and the epoch costs no register
+        // of its own
         int hd = 0;
-        constexpr int kOddBit = 1 << 30;
+        constexpr int kEpShift = 29, kEpMask = 3 << kEpShift;
+        // four epochs need every stale word to vanish in the rounding of the first scaled add: sums below 2^24 against
+        // scaled weights >= 2^50 (half an ulp: 2^26); a query that could exceed that (thousands of terms times a huge
+        // weight) runs its item with two epochs
+        const int ep_last = (kEpochs == 4 && (float)nq * a.max_weight < kEpochMaxSum) ? 3 : 1;
         auto issue = [&](const uint2 ds, StepBuf &b) {
             b.meta = ds.y;
             if ((int32_t)ds.y < 0) {  // wide flag; the same word in every lane: a uniform branch, cheaper than a vote + guard
@@ -659,12 +676,26 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
         // of the loop is warp-uniform) and the shared-memory pipe runs one warp's instructions in order, so a step's
         // stores land before the next step's loads; the asm statements carry "memory" clobbers, so the compiler keeps
         // the order too.
-        // SIGN EPOCHS (halves the re-zeroing, 39% of the shared-memory wavefronts in ncu): a sub-tile that follows an
-        // unscanned one is an ODD epoch -- the tile still holds the previous sub-tile's (positive) sums, the new sums
-        // are accumulated NEGATED (v = min(word, -0) - w: a stale positive word reads as -0; negation commutes with
-        // fp32 rounding, so -v is bit-identical to the plain sum) and only the END of an odd epoch re-zeroes the tile.
-        auto rmw = [&](const StepBuf &b, auto odd_c) {
-            constexpr bool ODD = decltype(odd_c)::value;
+        // TILE EPOCHS (re-zeroing 8 KB per sub-tile was 39% of the shared-memory wavefronts in ncu).  A sub-tile that
+        // follows an UNSCANNED one does not start from a zeroed tile; it accumulates in a form that makes every stale
+        // word read as zero, at no extra instruction:
+        //   epoch 0   v = x + w                         tile zeroed before
+        //   epoch 1   v = min(x, -0) - w                stale words are positive: they read as -0
+        //   epoch 2   v = fma(-w, 2^80, min(x, -0))     stale positives read as -0; stale NEGATIVE sums (epoch 1, > -2^24)
+        //                                               vanish in the rounding of the first add (-w 2^80 <= -2^50)
+        //   epoch 3   v = fma(w, 2^80, max(x, +0))      stale negatives (small or scaled) read as +0, small positives vanish
+        // Negation and scaling by a power of two commute with fp32 rounding (no overflow: sums stay below 2^104; no
+        // underflow: weights >= 2^-30), so the de-scaled sum is bit-identical to the plain one.  The tile is re-zeroed
+        // at the end of the last epoch (every 4th sub-tile; every 2nd in the two-epoch variants) or by a scan.
+        auto acc = [&](float x, float w, auto ep_c) -> float {
+            constexpr int EP = decltype(ep_c)::value;
+            if (EP == 0) return x + w;
+            if (EP == 1) return fminf(x, -0.f) - w;
+            if (EP == 2) return fmaf(-w, kEpochScale, fminf(x, -0.f));
+            return fmaf(w, kEpochScale, fmaxf(x, 0.f));
+        };
+        auto rmw = [&](const StepBuf &b, auto ep_c) {
+            constexpr bool NEG = decltype(ep_c)::value == 1 || decltype(ep_c)::value == 2;   // sums are negative
             if ((int32_t)b.meta < 0) {
                 const uint32_t oo[4] = {b.d.x, b.d.y, b.d.z, b.d.w};
                 const float ww[4] = {b.w.x, b.w.y, b.w.z, b.w.w};
@@ -672,17 +703,17 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
 #pragma unroll
                 for (int x = 0; x < 4; ++x) v[x] = lds_f32(tile_sa + oo[x]);
 #pragma unroll
-                for (int x = 0; x < 4; ++x) v[x] = ODD ? fminf(v[x], -0.f) - ww[x] : v[x] + ww[x];
+                for (int x = 0; x < 4; ++x) v[x] = acc(v[x], ww[x], ep_c);
 #pragma unroll
                 for (int x = 0; x < 4; ++x) sts_f32(tile_sa + oo[x], v[x]);
-                mx = ODD ? fminf(fminf(mx, v[0]), fminf(fminf(v[1], v[2]), v[3])) : fmaxf(fmaxf(mx, v[0]), fmaxf(fmaxf(v[1], v[2]), v[3]));
+                mx = NEG ? fminf(fminf(mx, v[0]), fminf(fminf(v[1], v[2]), v[3])) : fmaxf(fmaxf(mx, v[0]), fmaxf(fmaxf(v[1], v[2]), v[3]));
             } else {
                 const uint32_t o = b.d.x;
                 const float x = lds_f32(tile_sa + o);
                 const float w = __uint_as_float(b.d.y);  // narrow step: (offset, weight) = (d.x, d.y)
-                const float v = ODD ? fminf(x, -0.f) - w : x + w;
+                const float v = acc(x, w, ep_c);
                 sts_f32(tile_sa + o, v);
-                mx = ODD ? fminf(mx, v) : fmaxf(mx, v);
+                mx = NEG ? fminf(mx, v) : fmaxf(mx, v);
             }
         };
         // ---- end of a sub-tile: select from it (padding words only ever hold +-0) and, if needed, re-zero it
@@ -700,8 +731,10 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
             // threshold-on-update: scores only grow and weights are >= 0, so a document can enter the list only if
             // one of its updates reached the running k-th score; that happens in well under 1% of the sub-tiles
             // once a threshold exists
-            const bool odd = (hd & kOddBit) != 0;
-            const float peak = odd ? -mx : mx;
+            const int ep = (hd >> kEpShift) & 3;
+            // de-scaling factor of this epoch's sums (negative: the sums are stored negated)
+            const float unscale = (ep == 1 || ep == 2 ? -1.f : 1.f) * (ep >= 2 ? kEpochUnscale : 1.f);
+            const float peak = mx * unscale;
             bool scan = __any_sync(PR_FULL_MASK, peak >= thr);
             if (scan) {
                 // about to scan: first look at what other warps published since this item started -- only when items of
@@ -720,25 +753,29 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                 if (REFRESH) theta_pub = fmaxf(theta_pub, t);
             }
             if (!scan) {
-                if (odd || !PR_LEAN_SIGN_EPOCH) {
+                if (ep == ep_last || !PR_LEAN_SIGN_EPOCH) {
 #pragma unroll
                     for (int vv = lane & 31; vv < kSub / 4; vv += 32) tile4[vv] = zero4;
-                    hd &= ~kOddBit;
+                    hd &= ~kEpMask;
                 } else {
-                    hd |= kOddBit;  // leave the sums where they are: the next sub-tile accumulates negated
+                    hd += 1 << kEpShift;  // leave the sums where they are: the next sub-tile accumulates in the next form
                 }
             } else {
                 // `thr` is read live: it rises with every insert (the k-th score of the item's list), and a document below
                 // it can no longer enter the list -- in a launch without thresholds this cuts the candidates visited in an
                 // item's first sub-tile from every positive score (~450) to a few dozen.  The visiting order does not
                 // matter: the list is the top-k under a total order (score desc, doc id asc).
-                const float sgn = odd ? -1.f : 1.f;
+                // de-scaled words: this epoch's sums come out as the plain positive sums; stale words come out negative
+                // (never selected) or, in the scaled epochs, as positive dust below 2^-56 that the cut sets to zero.
+                // (Two copies of this loop, one without the cut for the unscaled epochs, measured slower: code size.)
+                const float cut = ep >= 2 ? kEpochCut : -1.f;
 #pragma unroll 4
                 for (int vv = lane & 31; vv < kSub / 4; vv += 32) {
                     const float4 xb = tile4[vv];
                     tile4[vv] = zero4;
-                    // odd epoch: current sums are negative, stale ones positive (-> negative here: never selected)
-                    const float xs[4] = {xb.x * sgn, xb.y * sgn, xb.z * sgn, xb.w * sgn};
+                    float xs[4] = {xb.x * unscale, xb.y * unscale, xb.z * unscale, xb.w * unscale};
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) xs[cc] = xs[cc] >= cut ? xs[cc] : 0.f;
                     const float m4 = fmaxf(fmaxf(xs[0], xs[1]), fmaxf(xs[2], xs[3]));
                     if (__any_sync(PR_FULL_MASK, m4 >= thr)) {
 #pragma unroll
@@ -752,7 +789,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                         }
                     }
                 }
-                hd &= ~kOddBit;
+                hd &= ~kEpMask;
             }
             mx = 0.f;
             if (REFRESH && iks > theta_pub) {  // this item alone holds k documents scoring >= iks: tell everyone scoring this query
@@ -762,13 +799,13 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
             __syncwarp();
         };
         // ---- one round of the ring: kPipe steps, each followed by the load of the step kPipe ahead
-        auto round = [&](auto odd_c) -> uint32_t {
+        auto round = [&](auto ep_c) -> uint32_t {
             uint32_t meta_last = 0u;
 #pragma unroll
             for (int d = 0; d < kPipe; ++d) {
                 const uint2 ds = lds_u2(slot(hd + d + kPipe));  // read early: its latency hides behind this step
                 if (d == kPipe - 1) meta_last = buf[d].meta;
-                rmw(buf[d], odd_c);
+                rmw(buf[d], ep_c);
                 issue(ds, buf[d]);
             }
             hd += kPipe;
@@ -788,18 +825,34 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                 for (int d = 0; d < kPipe; ++d) issue(lds_u2(slot(d)), buf[d]);
             }
             if (have_cur) {
+                // The epoch only changes at the end of a sub-tile, so it is dispatched once per sub-tile, not once per
+                // round: each epoch has its own tight loop of rounds that runs until a round ends on an END or LAST step
+                // (both only ever sit in the last slot of a round).
                 uint32_t meta_last;
+                auto rounds = [&](auto ep_c) -> uint32_t {
+                    uint32_t m;
+#pragma unroll 1
+                    do {
+                        m = round(ep_c);
+                    } while (!(m & (kFlagEnd | kFlagLast)));
+                    return m;
+                };
 #pragma unroll 1
                 do {
-                    meta_last = (hd & kOddBit) ? round(std::true_type{}) : round(std::false_type{});
-                    // END and "last step of the list" only ever sit in the last slot of a round
+                    if (kEpochs == 2) {
+                        meta_last = (hd & kEpMask) ? rounds(std::integral_constant<int, 1>{}) : rounds(std::integral_constant<int, 0>{});
+                    } else if (hd & (2 << kEpShift)) {
+                        meta_last = (hd & (1 << kEpShift)) ? rounds(std::integral_constant<int, 3>{}) : rounds(std::integral_constant<int, 2>{});
+                    } else {
+                        meta_last = (hd & (1 << kEpShift)) ? rounds(std::integral_constant<int, 1>{}) : rounds(std::integral_constant<int, 0>{});
+                    }
                     if (meta_last & kFlagEnd) end_subtile(meta_last);
                 } while (!(meta_last & kFlagLast));
             }
             have_cur = n_next > 0;
             if (!have_cur) break;
         }
-        if (hd & kOddBit) {  // the item ended on an unscanned even epoch: leave a clean tile for the next item
+        if (hd & kEpMask) {  // the item ended on unscanned sub-tiles: leave a clean tile for the next item
 #pragma unroll
             for (int vv = lane & 31; vv < kSub / 4; vv += 32) tile4[vv] = zero4;
             __syncwarp();

@@ -64,6 +64,7 @@ struct ScoreArgs {
     int64_t n_q_terms;
     int32_t n_docs, n_terms, doc_id_base, n_queries, K;
     int32_t n_sub, subs_per_item, chunk0, n_chunks_launch;
+    float max_weight;                       // largest weight of the index (bounds a query's scores: n_terms * max_weight)
 };
 
 // ---------------------------------------------------------------- index-side tables (aux)

@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 
 SCORE_RTOL = 1e-5
 
-DEFAULTS = dict(subs_per_item=24, warps_per_cta=8, docs_per_launch=393216, min_items=32768, items_per_warp=1)
+DEFAULTS = dict(subs_per_item=24, warps_per_cta=8, docs_per_launch=393216, min_items=32768, items_per_warp=1, tile_epochs=4, batch_variant=3)
 
 # launch plans that exercise every path of the live-threshold protocol (bm25_lean.cuh): one launch with all
 # thresholds travelling between warps, one chunk per launch (thresholds only through the merge), everything between
@@ -31,6 +31,13 @@ TUNINGS = [
     dict(subs_per_item=24, warps_per_cta=8, items_per_warp=64),                           # items cut down to one sub-tile, one launch
     dict(subs_per_item=2, warps_per_cta=8, docs_per_launch=8192, min_items=1, items_per_warp=1),
     dict(subs_per_item=24, warps_per_cta=8, docs_per_launch=49152, min_items=1, items_per_warp=1),  # long items, 3 launches
+    # the large-batch kernel variants (what a 65,536-query batch runs) on these small batches: four and two tile epochs
+    dict(batch_variant=2),
+    dict(batch_variant=2, tile_epochs=2),
+    dict(batch_variant=2, subs_per_item=7, warps_per_cta=12, docs_per_launch=30000, min_items=1),
+    dict(batch_variant=2, subs_per_item=1, warps_per_cta=4, docs_per_launch=2048, min_items=1, items_per_warp=1),
+    dict(batch_variant=2, subs_per_item=24, warps_per_cta=8, docs_per_launch=49152, min_items=1, tile_epochs=2),
+    dict(batch_variant=1, subs_per_item=24, docs_per_launch=49152, min_items=1),          # small-batch variant over several launches
 ]
 
 
@@ -126,6 +133,23 @@ def test_single_query_over_many_sub_tiles_uses_the_wide_merge():
             assert_parity(gs, gd, os_[:b], od[:b])
 
 
+def test_large_batch_takes_the_large_batch_variant(small_corpus, corpus_gpu):
+    """8,192 queries (more than twice the resident warps): the library picks the large-batch kernel variant by
+    itself -- four tile epochs, bounds published once per item -- over one and over many launches."""
+    idx = small_corpus["index"]
+    qi, qt = synth.queries_np(8192, small_corpus["vocab"], idx["df"], seed=99)
+    os_, od = co.retrieve_batch(idx, qi, qt, 10, n_threads=8)
+    for tun in (dict(), dict(docs_per_launch=8192, min_items=1), dict(tile_epochs=2, docs_per_launch=16384, min_items=1),
+                dict(subs_per_item=5, warps_per_cta=12, docs_per_launch=40000, min_items=1)):
+        tune(corpus_gpu, **tun)
+        gs, gd = run_gpu(corpus_gpu, qi, qt, 10)
+        assert_parity(gs, gd, os_, od)
+    os_, od = co.retrieve_batch(idx, qi, qt, 100, n_threads=8)
+    tune(corpus_gpu, docs_per_launch=16384, min_items=1)
+    gs, gd = run_gpu(corpus_gpu, qi, qt, 100)
+    assert_parity(gs, gd, os_, od)
+
+
 def test_long_transcript_queries(small_corpus, corpus_gpu):
     """Later-round queries are whole LM transcripts (exp_rag.py:428, 457): 64-1024 terms,
     many 32-term passes per sub-tile, posting cursors in the warp's scratch."""
@@ -134,7 +158,8 @@ def test_long_transcript_queries(small_corpus, corpus_gpu):
     assert np.diff(qi).max() > 256
     os_, od = co.retrieve_batch(idx, qi, qt, 10, n_threads=8)
     for tun in (dict(), dict(subs_per_item=4, docs_per_launch=98304, min_items=2048),
-                dict(subs_per_item=4, docs_per_launch=16384, min_items=1, items_per_warp=1)):
+                dict(subs_per_item=4, docs_per_launch=16384, min_items=1, items_per_warp=1),
+                dict(batch_variant=2), dict(batch_variant=2, tile_epochs=2, subs_per_item=4, docs_per_launch=16384, min_items=1)):
         tune(corpus_gpu, **tun)
         gs, gd = run_gpu(corpus_gpu, qi, qt, 10)
         assert_parity(gs, gd, os_, od)
@@ -266,7 +291,9 @@ def test_tie_heavy_corpus():
         for tun in (dict(), dict(subs_per_item=2, warps_per_cta=4, docs_per_launch=4096, min_items=1, items_per_warp=1),
                     dict(subs_per_item=12, warps_per_cta=8, docs_per_launch=98304, min_items=2048),
                     dict(subs_per_item=1, warps_per_cta=12, items_per_warp=64),
-                    dict(subs_per_item=3, warps_per_cta=8, docs_per_launch=8192, min_items=2048)):
+                    dict(subs_per_item=3, warps_per_cta=8, docs_per_launch=8192, min_items=2048),
+                    dict(batch_variant=2), dict(batch_variant=2, tile_epochs=2, docs_per_launch=8192, min_items=1),
+                    dict(batch_variant=2, subs_per_item=1, docs_per_launch=4096, min_items=1)):
             tune(gi, **tun)
             for _ in range(3):                      # the order in which warps publish bounds varies from run to run
                 gs, gd = run_gpu(gi, qi, qt, k)
@@ -335,7 +362,8 @@ def test_threshold_exchange_between_shards_keeps_the_merged_lists_bit_identical(
     shards = build_shards(small_corpus, g)
     nq, k = len(qi) - 1, 10
     L = _lib.lib()
-    for tun in (dict(subs_per_item=2, docs_per_launch=4096, min_items=1, items_per_warp=1), dict(docs_per_launch=16384, min_items=1, subs_per_item=4)):
+    for tun in (dict(subs_per_item=2, docs_per_launch=4096, min_items=1, items_per_warp=1), dict(docs_per_launch=16384, min_items=1, subs_per_item=4),
+                dict(batch_variant=2, docs_per_launch=16384, min_items=1, subs_per_item=4)):
         outs, calls, thetas = [], [], []
         for gi in shards:
             tune(gi, **tun)
@@ -423,7 +451,7 @@ def test_full_size_21m_properties():
     tune(gi)
     s2, d2 = gi.topk(d_qi, d_qt, 10)
     for tun in (dict(docs_per_launch=49152, min_items=1), dict(subs_per_item=6, warps_per_cta=12),
-                dict(docs_per_launch=4000000, warps_per_cta=4)):
+                dict(docs_per_launch=4000000, warps_per_cta=4), dict(batch_variant=2), dict(batch_variant=2, tile_epochs=2)):
         tune(gi, **tun)
         s1, d1 = gi.topk(d_qi, d_qt, 10)
         assert torch.equal(s1, s2) and torch.equal(d1, d2), tun
@@ -452,7 +480,8 @@ def test_extreme_weights(small_corpus):
     gi = gpu_index(idx)
     qi, qt = small_corpus["q_indptr"][:129], small_corpus["q_terms"]
     os_, od = co.retrieve_batch(idx, qi, qt, 10, n_threads=8)
-    for tun in (dict(), dict(docs_per_launch=16384, min_items=1)):
+    assert gi.get_tuning()["tile_epochs"] == 4          # asked for, but the weight range forbids it: the library runs two
+    for tun in (dict(), dict(docs_per_launch=16384, min_items=1), dict(batch_variant=2), dict(batch_variant=2, docs_per_launch=16384, min_items=1)):
         tune(gi, **tun)
         gs, gd = run_gpu(gi, qi, qt, 10)
         assert_parity(gs, gd, os_, od)
@@ -482,7 +511,9 @@ def test_random_shapes(seed):
     for k in (1, min(10, n_docs), min(100, n_docs)):
         os_, od = co.retrieve_batch(idx, qi, qt, k, n_threads=8)
         for tun in (dict(), dict(subs_per_item=1, warps_per_cta=4, docs_per_launch=2048, min_items=1, items_per_warp=1),
-                    dict(subs_per_item=2, warps_per_cta=12, docs_per_launch=4096, min_items=1, items_per_warp=1)):
+                    dict(subs_per_item=2, warps_per_cta=12, docs_per_launch=4096, min_items=1, items_per_warp=1),
+                    dict(batch_variant=2), dict(batch_variant=2, subs_per_item=1, docs_per_launch=2048, min_items=1),
+                    dict(batch_variant=2, tile_epochs=2, subs_per_item=3, docs_per_launch=6144, min_items=1)):
             tune(gi, **tun)
             gs, gd = run_gpu(gi, qi, qt, k)
             assert_parity(gs, gd, os_, od)

@@ -70,13 +70,26 @@ __device__ __forceinline__ void merge_lists(WarpTopK<E> &L, float &ks, int &kd, 
                 m &= m - 1;
                 const float *ps = ps0 + c * stride_c;
                 const int32_t *pd = pd0 + c * stride_c;
-                for (int i = 0; i < K; ++i) {
-                    const float bs = ps[i];
-                    const int bd = pd[i];
-                    if (bs < 0.f || bd < 0 || bs < floor) break;  // empty slot / missing entry / below the bound: list ends
-                    if (!pr_beats(bs, bd, ks, kd)) break;          // sorted: the rest lose too
-                    L.insert(bs, bd, lane);
-                    L.kth(K, ks, kd);
+                // the whole list in one coalesced load (lane i holds entry 32 e + i), then walked from registers: entry by
+                // entry it was up to K dependent L2 round trips per list
+                bool done = false;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int i0 = e * 32;
+                    if (done || i0 >= K) break;
+                    const float es = i0 + lane < K ? ps[i0 + lane] : -1.f;
+                    const int ed = i0 + lane < K ? pd[i0 + lane] : -1;
+                    const int n = min(32, K - i0);
+                    for (int i = 0; i < n; ++i) {
+                        const float bs = __shfl_sync(PR_FULL_MASK, es, i);
+                        const int bd = __shfl_sync(PR_FULL_MASK, ed, i);
+                        if (bs < 0.f || bd < 0 || bs < floor || !pr_beats(bs, bd, ks, kd)) {  // empty slot / missing entry /
+                            done = true;                                                    // below the bound / sorted: the
+                            break;                                                          // rest lose too
+                        }
+                        L.insert(bs, bd, lane);
+                        L.kth(K, ks, kd);
+                    }
                 }
             }
         }

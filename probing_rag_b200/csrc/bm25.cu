@@ -162,14 +162,63 @@ __global__ void __launch_bounds__(kWideWarps * 32) bm25_merge_wide_kernel(
     extern __shared__ __align__(16) unsigned char merge_smem[];
     float *sh_s = reinterpret_cast<float *>(merge_smem);                    // [kWideWarps][K]
     int32_t *sh_d = reinterpret_cast<int32_t *>(sh_s + kWideWarps * K);
+    __shared__ float s_floor;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = blockIdx.x;
-    const float floor = theta[q];
+    const float *ps0 = part_s + q * stride_q;
+    const int32_t *pd0 = part_d + q * stride_q;
     WarpTopK<E> L;
-    L.reset();
     float ks = PR_SENT_SCORE;
     int kd = PR_SENT_DOC;
-    merge_lists<E>(L, ks, kd, part_s + q * stride_q, part_d + q * stride_q, stride_c, warp, kWideWarps, C, K, floor, lane);
+    // Phase A: a bound from the list HEADS alone.  The heads are distinct documents, so the K-th largest head is a lower
+    // bound of the final K-th score -- far stronger than theta[q] here, which is only the best K-th score of a single
+    // short item (a single query over 21M documents: items of 6,144 documents).  With it phase B walks about K lists in
+    // total instead of a sizeable share of the thousands (one dependent L2 round trip each: 30 us at k = 10).
+    L.reset();
+    for (int c0 = warp; c0 < C; c0 += 32 * kWideWarps) {
+        const int cl = c0 + lane * kWideWarps;
+        float hs = -1.f;
+        int hd = -1;
+        if (cl < C) {
+            hs = ps0[cl * stride_c];
+            hd = pd0[cl * stride_c];
+        }
+        unsigned m = __ballot_sync(PR_FULL_MASK, hs >= 0.f && hd >= 0 && pr_beats(hs, hd, ks, kd));
+        while (m) {
+            const int l = __ffs(m) - 1;
+            m &= m - 1;
+            const float bs = __shfl_sync(PR_FULL_MASK, hs, l);
+            const int bd = __shfl_sync(PR_FULL_MASK, hd, l);
+            if (pr_beats(bs, bd, ks, kd)) {
+                L.insert(bs, bd, lane);
+                L.kth(K, ks, kd);
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = e * 32 + lane;
+        if (i < K) {
+            sh_s[warp * K + i] = L.s[e];
+            sh_d[warp * K + i] = L.d[e];
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        L.reset();
+        ks = PR_SENT_SCORE;
+        kd = PR_SENT_DOC;
+        merge_lists<E>(L, ks, kd, sh_s, sh_d, K, 0, 1, kWideWarps, K, -1.f, lane);
+        if (lane == 0) s_floor = fmaxf(theta[q], ks);   // (ks = -1 while fewer than K heads exist)
+    }
+    __syncthreads();
+    const float floor = s_floor;
+    __syncthreads();   // (sh_s / sh_d are reused below)
+    // Phase B: every warp folds its share of the lists, entries below the bound never looked at
+    L.reset();
+    ks = PR_SENT_SCORE;
+    kd = PR_SENT_DOC;
+    merge_lists<E>(L, ks, kd, ps0, pd0, stride_c, warp, kWideWarps, C, K, floor, lane);
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const int i = e * 32 + lane;

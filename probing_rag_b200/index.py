@@ -174,15 +174,35 @@ class BM25Index:
         self.weights.cpu().numpy().tofile(os.path.join(path, "weights.f32"))
 
     @classmethod
-    def load(cls, path: str, device="cuda") -> "BM25Index":
+    def load(cls, path: str, device="cuda", doc_range: tuple[int, int] | None = None) -> "BM25Index":
+        """Load a saved index.  `doc_range=(lo, hi)` cuts the doc-range shard [lo, hi) out of a saved WHOLE-corpus
+        index on the device: a term's postings are ascending in doc id, so the shard's list is a
+        contiguous piece of it, and the weights already carry the global N / avgdl / df -- they are the shard's
+        weights bit for bit."""
         with open(os.path.join(path, "index.json")) as f:
             hdr = json.load(f)
         if hdr.get("format") != "probing-rag-b200-csr-v1":
             raise ValueError(f"{path}: not a probing-rag-b200 index")
         dev = torch.device(device)
         ld = lambda name, dt: torch.from_numpy(np.fromfile(os.path.join(path, name), dtype=dt)).to(dev)
-        return cls(ld("indptr.i64", np.int64), ld("doc_ids.i32", np.int32), ld("weights.f32", np.float32),
-                   hdr["n_docs"], hdr["n_docs_global"], hdr["doc_id_base"], meta=hdr.get("meta"))
+        indptr, doc_ids, weights = ld("indptr.i64", np.int64), ld("doc_ids.i32", np.int32), ld("weights.f32", np.float32)
+        if doc_range is None:
+            return cls(indptr, doc_ids, weights, hdr["n_docs"], hdr["n_docs_global"], hdr["doc_id_base"], meta=hdr.get("meta"))
+        lo, hi = int(doc_range[0]), int(doc_range[1])
+        if hdr["doc_id_base"] != 0 or hdr["n_docs"] != hdr["n_docs_global"]:
+            raise ValueError(f"{path} holds a shard already; doc_range cuts shards out of a whole-corpus index")
+        if not 0 <= lo <= hi <= hdr["n_docs"]:
+            raise ValueError(f"doc_range [{lo}, {hi}) outside [0, {hdr['n_docs']})")
+        keep = (doc_ids >= lo) & (doc_ids < hi)
+        # postings kept per term = difference of the running count of kept postings at the term boundaries
+        run = torch.zeros(doc_ids.numel() + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(keep, 0, out=run[1:])
+        s_indptr = run[indptr]
+        del run
+        s_docs = (doc_ids[keep] - lo).to(torch.int32)
+        s_w = weights[keep]
+        del keep, doc_ids, weights
+        return cls(s_indptr, s_docs, s_w, hi - lo, hdr["n_docs_global"], lo, meta=hdr.get("meta"))
 
     # ------------------------------------------------------------------ tuning
     def set_tuning(self, **kw) -> None:

@@ -253,7 +253,12 @@ class BM25Retriever:
 
     @classmethod
     def from_persist_dir(cls, path: str, device="cuda", similarity_top_k: int | None = None,
-                         stemmer=None) -> "BM25Retriever":
+                         stemmer=None, sharded: bool = False, group=None, exchange="p2p",
+                         max_queries: int = 65536) -> "BM25Retriever":
+        """Load a persisted retriever.  `sharded=True` (one process per GPU, `torch.distributed` initialised): every
+        rank cuts ITS doc-range shard out of the saved whole-corpus index (`BM25Index.load(doc_range=…)`) and the
+        retriever scores through `sharding.ShardedBM25` -- every rank returns the same merged lists, with texts from
+        the memory-mapped passage store all ranks share."""
         with open(os.path.join(path, RETRIEVER_JSON)) as f:
             cfg = json.load(f)
         if cfg.get("format") != "probing-rag-b200-retriever-v1":
@@ -263,7 +268,18 @@ class BM25Retriever:
         if have != cfg.get("stemmer"):
             raise ValueError(f"{path} was indexed with stemmer {cfg.get('stemmer')!r} but this process has {have!r}: "
                              "query stems would not match the vocabulary")
-        index = BM25Index.load(path, device=device)
+        if sharded:
+            import torch.distributed as dist
+
+            from .sharding import ShardedBM25, shard_range
+            with open(os.path.join(path, "index.json")) as f:
+                n_docs = json.load(f)["n_docs"]
+            rng = shard_range(n_docs, dist.get_rank(group), dist.get_world_size(group))
+            shard = BM25Index.load(path, device=device, doc_range=rng)
+            index = ShardedBM25(shard, group=group, exchange=exchange, max_queries=max_queries)
+            index.n_terms = shard.n_terms
+        else:
+            index = BM25Index.load(path, device=device)
         if index.n_terms != max(len(vocab), 1):
             raise ValueError(f"{path}: vocabulary of {len(vocab)} stems for an index of {index.n_terms} terms")
         meta = None

@@ -414,6 +414,34 @@ def test_save_load_roundtrip(tmp_path, small_corpus, corpus_gpu):
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
 
 
+def test_shards_cut_from_a_saved_whole_index_equal_shards_built_from_the_corpus(tmp_path, small_corpus, corpus_gpu):
+    """BM25Index.load(doc_range=...): the doc-range shard of a persisted whole-corpus index has exactly the arrays of a
+    shard built from its documents with the global statistics, including empty and one-document ranges."""
+    from probing_rag_b200 import BM25Index, merge_topk
+    corpus_gpu.save(str(tmp_path / "ix"))
+    idx, toks, lens = small_corpus["index"], small_corpus["tokens"], small_corpus["doc_lens"]
+    off = np.concatenate([[0], np.cumsum(lens, dtype=np.int64)])
+    n_docs = len(lens)
+    qi, qt = small_corpus["q_indptr"][:129], small_corpus["q_terms"]
+    ref_s, ref_d = co.retrieve_batch(idx, qi, qt, 10, n_threads=8)
+    ss, dd = [], []
+    for lo, hi in ((0, 33334), (33334, 33335), (33335, 33335), (33335, 90000), (90000, n_docs)):
+        sh = BM25Index.load(str(tmp_path / "ix"), doc_range=(lo, hi))
+        want = bo.build_index(toks[off[lo]:off[hi]], lens[lo:hi], small_corpus["vocab"], n_docs_global=n_docs,
+                              avgdl_global=idx["avgdl"], df_global=idx["df"], doc_id_base=lo)
+        assert (sh.n_docs, sh.n_docs_global, sh.doc_id_base) == (hi - lo, n_docs, lo)
+        assert np.array_equal(sh.indptr.cpu().numpy(), want["indptr"])
+        assert np.array_equal(sh.doc_ids.cpu().numpy(), want["indices"])
+        assert np.array_equal(sh.weights.cpu().numpy(), want["data"])
+        s, d = sh.topk(*to_dev(sh, qi, qt), 10)
+        ss.append(s); dd.append(d)
+    ms, md = merge_topk(torch.stack(ss), torch.stack(dd))
+    torch.cuda.synchronize()
+    assert_parity(ms.cpu().numpy(), md.cpu().numpy(), ref_s, ref_d)
+    with pytest.raises(ValueError):
+        BM25Index.load(str(tmp_path / "ix"), doc_range=(5, n_docs + 1))
+
+
 def test_retriever_text_level_drop_in():
     """exp_rag.py:242 / :426 / :372 shape: from_defaults(docstore=...), retrieve(str) -> nodes with
     .text/.score, score-descending; checked against the oracle on the same token ids."""

@@ -2,6 +2,7 @@
 threshold exchange between launches, all-gather + merge -- the merged lists must be bit-identical to the
 single-index lists AND to the CPU oracle.  Skipped on a box with one GPU (the gloo tests cover the host logic
 there, tests/test_gpu_bm25.py the exchange protocol itself)."""
+import json
 import os
 import socket
 
@@ -12,6 +13,16 @@ import torch
 pytestmark = pytest.mark.gpu
 
 N_DOCS, VOCAB, NQ = 300_000, 1 << 18, 512
+
+
+TEXT_QUERIES = ["paris tower capital", "river bridge london", "", "probing hidden states of language models"]
+
+
+def _texts():
+    rng = np.random.default_rng(17)
+    words = ("retrieval augmented generation probing language model hidden state wikipedia passage question answer paris "
+             "france capital city river tower london england bridge").split()
+    return [" ".join(rng.choice(words, size=int(rng.integers(3, 30)))) for _ in range(5000)]
 
 
 def _free_port():
@@ -48,6 +59,17 @@ def _worker(rank, world, port, out_dir):
                 assert d2h == NQ * k * 8
                 res[f"{name}_s{k}"], res[f"{name}_d{k}"] = hs, hd
             sb.close()
+        # the persisted text-level retriever, loaded sharded: every rank cuts its doc range out of the saved index
+        from probing_rag_b200 import BM25Retriever
+        if rank == 0:
+            BM25Retriever.from_texts(iter(_texts()), similarity_top_k=4, device=dev, persist_dir=os.path.join(out_dir, "text_ix"))
+        dist.barrier()
+        tr = BM25Retriever.from_persist_dir(os.path.join(out_dir, "text_ix"), device=dev, sharded=True, max_queries=64)
+        assert tr.index.exchange == "p2p" and tr.index.index.n_docs < len(_texts())
+        rows = [[(n.node.id_, n.score, n.text) for n in one] for one in tr.retrieve_batch(TEXT_QUERIES)]
+        with open(os.path.join(out_dir, f"text_r{rank}.json"), "w") as f:
+            json.dump(rows, f)
+        tr.index.close()
         res["launches"] = np.array([gi.num_launches(NQ, 10)])
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), **res)
         with pytest.raises(ValueError):                 # bad term ids raise on the sharded path too
@@ -70,6 +92,12 @@ def test_nccl_doc_shards_equal_single_index_and_oracle(tmp_path, world):
     host = {"data": gi.weights.cpu().numpy(), "indices": gi.doc_ids.cpu().numpy(), "indptr": gi.indptr.cpu().numpy(),
             "num_docs": gi.n_docs}
     d_qi, d_qt = torch.from_numpy(qi).cuda(), torch.from_numpy(qt).cuda()
+    from probing_rag_b200 import BM25Retriever
+    single = BM25Retriever.from_persist_dir(str(tmp_path / "text_ix"))
+    want = [[[n.node.id_, n.score, n.text] for n in one] for one in single.retrieve_batch(TEXT_QUERIES)]
+    assert all(len(one) == 4 and all(x[2] for x in one) for one in want)
+    for r in range(world):
+        assert json.load(open(tmp_path / f"text_r{r}.json")) == want, f"rank {r}: sharded text retrieval differs"
     for k in (10, 100):
         s1, d1 = gi.topk(d_qi, d_qt, k)
         os_, od = co.retrieve_batch(host, qi, qt, k, n_threads=min(16, os.cpu_count() or 1))

@@ -12,7 +12,10 @@ be compared with PyStemmer in this container.
 """
 from __future__ import annotations
 
+import ctypes
+import os
 import re
+import unicodedata
 
 import numpy as np
 
@@ -183,11 +186,43 @@ def porter2_stem(word: str) -> str:
     return w.replace("Y", "y")
 
 
+_TEXT_LIB = None
+
+
+def _text_lib():
+    """libprtext.so (csrc/textproc.c): the corpus tokenizer in C.  None when it has not been built or was generated
+    from another Unicode database than this interpreter's -- the Python path below is then used for every document
+    (it is also what the C path hands the documents it cannot express exactly to)."""
+    global _TEXT_LIB
+    if _TEXT_LIB is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libprtext.so")
+        lib = False
+        if os.path.exists(path) and os.environ.get("PROBING_RAG_PY_TOKENIZER", "0") != "1":
+            lib = ctypes.CDLL(path)
+            c, vp, i64 = ctypes, ctypes.c_void_p, ctypes.c_int64
+            lib.pt_unidata_version.restype = c.c_char_p
+            lib.pt_create.restype = vp
+            lib.pt_destroy.argtypes = [vp]
+            lib.pt_size.restype, lib.pt_size.argtypes = i64, [vp]
+            lib.pt_encode.restype = i64
+            lib.pt_encode.argtypes = [vp, vp, vp, i64, i64, vp, i64, c.POINTER(i64), vp]
+            lib.pt_intern_many.restype, lib.pt_intern_many.argtypes = c.c_int, [vp, vp, vp, i64, vp]
+            lib.pt_tokens_since.restype, lib.pt_tokens_since.argtypes = i64, [vp, i64, vp, i64, vp]
+            lib.pt_stem_many.restype, lib.pt_stem_many.argtypes = None, [vp, vp, i64, vp, vp]
+            if lib.pt_unidata_version().decode() != unicodedata.unidata_version:
+                lib = False
+        _TEXT_LIB = lib
+    return _TEXT_LIB or None
+
+
 class BuiltinStemmer:
-    """PyStemmer-shaped object: `.stemWords(list[str]) -> list[str]`."""
+    """PyStemmer-shaped object: `.stemWords(list[str]) -> list[str]`.  Batches go through the C restatement of the
+    same algorithm (csrc/textproc.c:pt_stem_many) when libprtext.so is built; words with non-ASCII letters and
+    single words stay on `porter2_stem`."""
 
     def __init__(self):
         self._cache: dict[str, str] = {}
+        self._lib = _text_lib()
 
     def stemWord(self, word: str) -> str:
         s = self._cache.get(word)
@@ -196,7 +231,26 @@ class BuiltinStemmer:
         return s
 
     def stemWords(self, words):
-        return [self.stemWord(w) for w in words]
+        if self._lib is None or len(words) < 64:
+            return [self.stemWord(w) for w in words]
+        words = list(words)
+        idx = [i for i, w in enumerate(words) if w.isascii()]
+        enc = [words[i].encode("ascii") for i in idx]
+        n = len(enc)
+        offs = np.zeros(n + 1, np.int64)
+        np.cumsum(np.fromiter(map(len, enc), np.int64, n), out=offs[1:])
+        out = ctypes.create_string_buffer(int(offs[-1]) + 2 * n + 1)
+        oo = np.empty(n + 1, np.int64)
+        self._lib.pt_stem_many(b"".join(enc), offs.ctypes.data, n, out, oo.ctypes.data)
+        text = out.raw[:int(oo[-1])].decode("ascii")
+        ol = oo.tolist()
+        res = [None] * len(words)
+        for j, i in enumerate(idx):
+            res[i] = text[ol[j]:ol[j + 1]]
+        for i, w in enumerate(words):
+            if res[i] is None:
+                res[i] = self.stemWord(w)
+        return res
 
 
 def get_stemmer():
@@ -235,6 +289,13 @@ class Vocabulary:
         self._surf = _AutoId()                       # surface token -> surface id
         self._surf_stem = np.zeros(0, np.int32)      # surface id -> stem id, -1 = stop word
         self._n_mapped = 0
+        self._lib = _text_lib()
+        self._tab = self._lib.pt_create() if self._lib is not None else None   # C surface-token table
+
+    def __del__(self):
+        if getattr(self, "_tab", None):
+            self._lib.pt_destroy(self._tab)
+            self._tab = None
 
     def __len__(self) -> int:
         return len(self.stem_to_id)
@@ -263,9 +324,7 @@ class Vocabulary:
         self._surf_stem[self._n_mapped:n] = out
         self._n_mapped = n
 
-    def encode_corpus_batch(self, texts) -> tuple[np.ndarray, np.ndarray]:
-        """Documents -> (term ids i32[total], doc lengths i32[n]), docs back to back; new
-        stems are added to the vocabulary."""
+    def _surface_ids_py(self, texts):
         find = TOKEN_PATTERN.findall
         toks, counts = [], []
         for t in texts:
@@ -273,6 +332,68 @@ class Vocabulary:
             toks.extend(w)
             counts.append(len(w))
         sid = np.fromiter(map(self._surf.__getitem__, toks), dtype=np.int64, count=len(toks))
+        return sid, np.asarray(counts, np.int64)
+
+    def _surface_ids_c(self, texts):
+        """The same (surface ids, tokens per document) through csrc/textproc.c.  Documents the C tables cannot
+        express exactly (see its header) go through `re` here, one at a time and in place, so surface ids keep
+        their first-seen order; the new surface strings are copied back into `self._surf` afterwards (the query
+        side and the stemmer work on Python strings)."""
+        lib, tab = self._lib, self._tab
+        enc = [t.encode("utf-8") for t in texts]
+        n = len(enc)
+        offs = np.zeros(n + 1, np.int64)
+        np.cumsum(np.fromiter(map(len, enc), np.int64, n), out=offs[1:])
+        buf = b"".join(enc)
+        cap = len(buf) // 2 + 1                       # a token is at least two bytes
+        ids = np.empty(cap, np.int32)
+        counts = np.zeros(n, np.int32)
+        n_tok = ctypes.c_int64(0)
+        find = TOKEN_PATTERN.findall
+        i = 0
+        while i < n:
+            i = lib.pt_encode(tab, buf, offs.ctypes.data, i, n, ids.ctypes.data, cap, ctypes.byref(n_tok),
+                              counts.ctypes.data)
+            if i < 0:
+                raise MemoryError("libprtext: out of memory")
+            if i < n:                                 # this document needs str.lower() / re
+                w = [t.encode("utf-8") for t in find(texts[i].lower())]
+                if w:
+                    wo = np.zeros(len(w) + 1, np.int64)
+                    np.cumsum(np.fromiter(map(len, w), np.int64, len(w)), out=wo[1:])
+                    out = np.empty(len(w), np.int32)
+                    if lib.pt_intern_many(tab, b"".join(w), wo.ctypes.data, len(w), out.ctypes.data) != 0:
+                        raise MemoryError("libprtext: out of memory")
+                    if n_tok.value + len(w) > cap:    # cannot happen (>= 2 bytes per token), but never overrun
+                        raise RuntimeError("token buffer too small")
+                    ids[n_tok.value:n_tok.value + len(w)] = out
+                    n_tok.value += len(w)
+                counts[i] = len(w)
+                i += 1
+        have = len(self._surf)
+        total = lib.pt_size(tab)
+        if total > have:
+            nbytes = lib.pt_tokens_since(tab, have, None, 0, None)
+            raw = ctypes.create_string_buffer(max(int(nbytes), 1))
+            to = np.empty(total - have + 1, np.int64)
+            if lib.pt_tokens_since(tab, have, raw, nbytes, to.ctypes.data) != nbytes:
+                raise RuntimeError("libprtext: token table changed underneath")
+            text = raw.raw[:nbytes]
+            surf = self._surf
+            tl = to.tolist()
+            for j in range(total - have):
+                surf[text[tl[j]:tl[j + 1]].decode("utf-8")] = have + j
+        return ids[:n_tok.value].astype(np.int64), counts.astype(np.int64)
+
+    def encode_corpus_batch(self, texts) -> tuple[np.ndarray, np.ndarray]:
+        """Documents -> (term ids i32[total], doc lengths i32[n]), docs back to back; new
+        stems are added to the vocabulary."""
+        if not isinstance(texts, (list, tuple)):
+            texts = list(texts)
+        if self._tab is not None and len(self._surf) == self._lib.pt_size(self._tab):
+            sid, counts = self._surface_ids_c(texts)
+        else:                                         # no C library
+            sid, counts = self._surface_ids_py(texts)
         self._map_new_surfaces()
         stem = self._surf_stem[sid]
         keep = stem >= 0

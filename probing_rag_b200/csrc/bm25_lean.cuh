@@ -94,7 +94,8 @@ static_assert(2 * kListCap + kPipe <= kRing, "ring too small");
 static_assert(kListCap % kPipe == 0, "lists are whole rings of kPipe steps");
 
 // descriptor .y: bits 5..0 valid lanes of a narrow step, bit 6 end of sub-tile (sub-tile index in bits 30..8), bit 7 last
-// step of its list, bit 31 wide step (the sign bit: one ISETP tests it)
+// step of its list, bit 31 wide step (the sign bit: one ISETP tests it).  END and LAST are flags on whatever step sits
+// in the last slot of a round -- a real step or the no-op that pads the round
 enum : uint32_t { kFlagWide = 0x80000000u, kFlagEnd = 0x40, kFlagLast = 0x80 };  // kFlagLast: last step of a produced list
 constexpr int kCntShift = 0, kSubIdxShift = 8;
 
@@ -362,17 +363,23 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
         // what follows every list: kPipe no-ops for the look-ahead of the consumer (overwritten by the next list)
         // (`pos` = ring position behind the list, `len` = its length); the list's last step gets kFlagLast, which
         // ends the consumer's drain loop without a counter
-        auto finish_list = [&](int pos, int len) {
+        // `fold`: END flags for the list's last step when that step is a real one (see or_flags)
+        auto or_flags = [&](int pos, uint32_t flags) {  // one lane: descriptor .y at ring position pos |= flags
+            const uint32_t la = slot(pos) + 4u;
+            uint32_t y;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(y) : "r"(la) : "memory");
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(la), "r"(y | flags) : "memory");
+        };
+        auto finish_list = [&](int pos, int len, uint32_t fold = 0u) {
             if (lane < kPipe) sts_u2(slot(pos + lane), 0u, 0u);
             __syncwarp();
-            if (len > 0 && lane == 0) {
-                const uint32_t la = slot(pos - 1) + 4u;
-                uint32_t y;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(y) : "r"(la) : "memory");
-                asm volatile("st.shared.u32 [%0], %1;" ::"r"(la), "r"(y | (uint32_t)kFlagLast) : "memory");
-            }
+            if (len > 0 && lane == 0) or_flags(pos - 1, (uint32_t)kFlagLast | fold);
             __syncwarp();
         };
+        // THE END OF A SUB-TILE IS A FLAG, NOT A STEP, whenever the sub-tile's last real step falls into the last slot
+        // of a round (the consumer looks at the flags of that slot only): the END rides on that step.  Otherwise the
+        // no-op that pads the round carries it, as a count-0 narrow step.  (An END step of its own behind every
+        // sub-tile was 11% of all steps of a round-0 batch.)
 
         auto produce = [&](const int tl) -> int {
             while (it_g < sub1) {
@@ -479,16 +486,21 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                 if (chunk == 0 && !end) continue;  // nothing in this pass / untouched sub-tile
                 // ---- this lane's entries k in [k0, k1) -> list positions pre + k - w0
                 write_steps(tl + pre + max(0, w0 - pre) - w0, max(0, w0 - pre), min(n, w0 + chunk - pre), n_wide);
-                // ---- no-ops up to a multiple of kPipe; an END step always sits in the last ring slot
+                // ---- no-ops up to a multiple of kPipe; the END sits in the last ring slot
                 int len = chunk;
-                const int pad = (kPipe - ((len + (end ? 1 : 0)) % kPipe)) % kPipe;
-                if (lane < pad) sts_u2(slot(tl + len + lane), 0u, 0u);
-                len += pad;
-                if (end) {
-                    if (lane == 0) sts_u2(slot(tl + len), 0u, (uint32_t)kFlagEnd | ((uint32_t)g << kSubIdxShift));
-                    ++len;
+                uint32_t fold = 0u;
+                if (end && len > 0 && len % kPipe == 0) {
+                    fold = (uint32_t)kFlagEnd | ((uint32_t)g << kSubIdxShift);
+                } else {
+                    const int pad = (kPipe - ((len + (end ? 1 : 0)) % kPipe)) % kPipe;
+                    if (lane < pad) sts_u2(slot(tl + len + lane), 0u, 0u);
+                    len += pad;
+                    if (end) {
+                        if (lane == 0) sts_u2(slot(tl + len), 0u, (uint32_t)kFlagEnd | ((uint32_t)g << kSubIdxShift));
+                        ++len;
+                    }
                 }
-                finish_list(tl + len, len);
+                finish_list(tl + len, len, fold);
                 return len;
             }
             finish_list(tl, 0);
@@ -576,7 +588,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                     prev_e = e;
                     if (ss == 0) t0 = t;
                     if (t > 0) {
-                        const int total = (t + kPipe) / kPipe * kPipe;  // t steps + END, rounded up to whole rings
+                        const int total = (t + kPipe - 1) / kPipe * kPipe;  // t steps rounded up to whole rings; the END rides on the last slot
                         if (base + total > kListCap) {
                             chunked = ss == 0;
                             break;
@@ -593,15 +605,16 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                 if (!chunked) {
                     it_g = g0 + ns_eff;
                     if (base == 0) continue;  // the first non-empty sub-tile did not fit behind empty ones: next round
+                    // the END of the last sub-tile laid out is the list's last step: it carries kFlagLast itself
+                    const uint32_t end_flags = (uint32_t)kFlagEnd | ((uint32_t)g << kSubIdxShift) | (my_base + my_total == base ? (uint32_t)kFlagLast : 0u);
+                    const int pad = my_total - my_t;  // slots behind the last real step
                     if (my_base >= 0) {
                         write_steps(tl + my_base + pre, 0, n, n_wide);
-                        const int pad = my_total - my_t - 1;
-                        if (j < pad) sts_u2(slot(tl + my_base + my_t + j), 0u, 0u);
-                        // the END of the last sub-tile laid out is the list's last step: it carries kFlagLast itself
-                        if (j == TPL - 1)
-                            sts_u2(slot(tl + my_base + my_total - 1), 0u,
-                                   (uint32_t)kFlagEnd | ((uint32_t)g << kSubIdxShift) | (my_base + my_total == base ? (uint32_t)kFlagLast : 0u));
+                        if (j < pad - 1) sts_u2(slot(tl + my_base + my_t + j), 0u, 0u);
+                        if (j == TPL - 1 && pad > 0) sts_u2(slot(tl + my_base + my_total - 1), 0u, end_flags);
                     }
+                    __syncwarp();
+                    if (my_base >= 0 && j == TPL - 1 && pad == 0) or_flags(tl + my_base + my_total - 1, end_flags);
                     finish_list(tl + base, 0);  // (kFlagLast already set above)
                     return base;
                 }
@@ -618,14 +631,19 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                 }
                 if (s == 0) write_steps(tl + pre + max(0, w0 - pre) - w0, max(0, w0 - pre), min(n, w0 + chunk - pre), n_wide);
                 int len = chunk;
-                const int pad = (kPipe - ((len + (fin ? 1 : 0)) % kPipe)) % kPipe;
-                if (lane < pad) sts_u2(slot(tl + len + lane), 0u, 0u);
-                len += pad;
-                if (fin) {
-                    if (lane == 0) sts_u2(slot(tl + len), 0u, (uint32_t)kFlagEnd | ((uint32_t)g0 << kSubIdxShift));
-                    ++len;
+                uint32_t fold = 0u;
+                if (fin && len > 0 && len % kPipe == 0) {
+                    fold = (uint32_t)kFlagEnd | ((uint32_t)g0 << kSubIdxShift);
+                } else {
+                    const int pad = (kPipe - ((len + (fin ? 1 : 0)) % kPipe)) % kPipe;
+                    if (lane < pad) sts_u2(slot(tl + len + lane), 0u, 0u);
+                    len += pad;
+                    if (fin) {
+                        if (lane == 0) sts_u2(slot(tl + len), 0u, (uint32_t)kFlagEnd | ((uint32_t)g0 << kSubIdxShift));
+                        ++len;
+                    }
                 }
-                finish_list(tl + len, len);
+                finish_list(tl + len, len, fold);
                 return len;
             }
             finish_list(tl, 0);
@@ -718,7 +736,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
         };
         // ---- end of a sub-tile: select from it (padding words only ever hold +-0) and, if needed, re-zero it
         auto end_subtile = [&](const uint32_t meta) {
-            const int g_end = (int)(meta >> kSubIdxShift);
+            const int g_end = (int)((meta & ~(uint32_t)kFlagWide) >> kSubIdxShift);  // (the END may ride on a wide step)
             const int base_doc = (g_end << kSubShift) + a.doc_id_base;
             auto consider = [&](float bs, int off) {  // warp-uniform arguments, exact score
                 const int bd = base_doc + off;

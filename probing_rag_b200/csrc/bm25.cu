@@ -170,50 +170,79 @@ __global__ void __launch_bounds__(kWideWarps * 32) bm25_merge_wide_kernel(
     WarpTopK<E> L;
     float ks = PR_SENT_SCORE;
     int kd = PR_SENT_DOC;
-    // Phase A: a bound from the list HEADS alone.  The heads are distinct documents, so the K-th largest head is a lower
-    // bound of the final K-th score -- far stronger than theta[q] here, which is only the best K-th score of a single
-    // short item (a single query over 21M documents: items of 6,144 documents).  With it phase B walks about K lists in
-    // total instead of a sizeable share of the thousands (one dependent L2 round trip each: 30 us at k = 10).
-    L.reset();
-    for (int c0 = warp; c0 < C; c0 += 32 * kWideWarps) {
-        const int cl = c0 + lane * kWideWarps;
-        float hs = -1.f;
-        int hd = -1;
-        if (cl < C) {
-            hs = ps0[cl * stride_c];
-            hd = pd0[cl * stride_c];
-        }
-        unsigned m = __ballot_sync(PR_FULL_MASK, hs >= 0.f && hd >= 0 && pr_beats(hs, hd, ks, kd));
-        while (m) {
-            const int l = __ffs(m) - 1;
-            m &= m - 1;
-            const float bs = __shfl_sync(PR_FULL_MASK, hs, l);
-            const int bd = __shfl_sync(PR_FULL_MASK, hd, l);
-            if (pr_beats(bs, bd, ks, kd)) {
-                L.insert(bs, bd, lane);
-                L.kth(K, ks, kd);
+    // Phase A: a bound from the list HEADS alone.  The heads are distinct documents, so the K-th largest head score is a
+    // lower bound of the final K-th score -- far stronger than theta[q] here, which is only the best K-th score of a
+    // single short item (a single query over 21M documents: items of 6,144 documents).  With it phase B walks about K
+    // lists in total instead of a sizeable share of the thousands.  The K-th largest of the C head scores is found by a
+    // block-wide RADIX SELECT on the score bits (scores >= 0 order like their bit patterns): four passes of 8 bits, a
+    // 256-bin histogram in shared memory each.  (Folding the heads through per-warp register lists and then the 32
+    // lists through warp 0 was ~150 dependent insertions: 20 of the 27 us this kernel took for a single query.)
+    __shared__ int s_hist[256];
+    __shared__ uint32_t s_prefix;
+    __shared__ int s_remaining;
+    constexpr int kHeadRegs = 4;   // heads kept in registers (C <= 4096: every small batch on one GPU); the rest is re-read
+    constexpr uint32_t kNoKey = 0xffffffffu;
+    auto head_key = [&](int c) -> uint32_t {
+        const float hs = ps0[c * stride_c];
+        const int hd = pd0[c * stride_c];
+        return (hs >= 0.f && hd >= 0) ? __float_as_uint(hs) : kNoKey;
+    };
+    uint32_t hk[kHeadRegs];
+#pragma unroll
+    for (int r = 0; r < kHeadRegs; ++r) {
+        const int c = (int)threadIdx.x + r * kWideWarps * 32;
+        hk[r] = c < C ? head_key(c) : kNoKey;
+    }
+    uint32_t prefix = 0u;
+    int remaining = K;
+#pragma unroll 1
+    for (int shift = 24; shift >= 0 && remaining > 0; shift -= 8) {
+        if (threadIdx.x < 256) s_hist[threadIdx.x] = 0;
+        __syncthreads();
+        const uint32_t hi_mask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+        auto vote = [&](uint32_t key) {
+            if (key != kNoKey && (key & hi_mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1);
+        };
+#pragma unroll
+        for (int r = 0; r < kHeadRegs; ++r) vote(hk[r]);
+        for (int c = (int)threadIdx.x + kHeadRegs * kWideWarps * 32; c < C; c += kWideWarps * 32) vote(head_key(c));
+        __syncthreads();
+        if (warp == 0) {   // lane l holds bins 255 - 8 l ... 248 - 8 l: the bin in which the running count from the top reaches `remaining`
+            int cnt[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                cnt[j] = s_hist[255 - (lane * 8 + j)];
+                sum += cnt[j];
+            }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(PR_FULL_MASK, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int total = __shfl_sync(PR_FULL_MASK, incl, 31);
+            if (total < remaining) {   // fewer than K heads (only possible in the first pass): no bound from the heads
+                if (lane == 0) s_remaining = -1;
+            } else if (incl - sum < remaining && remaining <= incl) {
+                int cum = incl - sum;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (cum + cnt[j] >= remaining) {
+                        s_prefix = prefix | ((uint32_t)(255 - (lane * 8 + j)) << shift);
+                        s_remaining = remaining - cum;
+                        break;
+                    }
+                    cum += cnt[j];
+                }
             }
         }
+        __syncthreads();
+        prefix = s_prefix;
+        remaining = s_remaining;
     }
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const int i = e * 32 + lane;
-        if (i < K) {
-            sh_s[warp * K + i] = L.s[e];
-            sh_d[warp * K + i] = L.d[e];
-        }
-    }
-    __syncthreads();
-    if (warp == 0) {
-        L.reset();
-        ks = PR_SENT_SCORE;
-        kd = PR_SENT_DOC;
-        merge_lists<E>(L, ks, kd, sh_s, sh_d, K, 0, 1, kWideWarps, K, -1.f, lane);
-        if (lane == 0) s_floor = fmaxf(theta[q], ks);   // (ks = -1 while fewer than K heads exist)
-    }
+    if (threadIdx.x == 0) s_floor = remaining > 0 ? fmaxf(theta[q], __uint_as_float(prefix)) : theta[q];
     __syncthreads();
     const float floor = s_floor;
-    __syncthreads();   // (sh_s / sh_d are reused below)
     // Phase B: every warp folds its share of the lists, entries below the bound never looked at
     L.reset();
     ks = PR_SENT_SCORE;

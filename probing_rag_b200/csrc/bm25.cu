@@ -200,12 +200,19 @@ __global__ void __launch_bounds__(kWideWarps * 32) bm25_merge_wide_kernel(
         if (threadIdx.x < 256) s_hist[threadIdx.x] = 0;
         __syncthreads();
         const uint32_t hi_mask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+        // one shared-memory atomic per (warp, bin): the scores of a query share their exponent, so in the first passes
+        // every key falls into the same one or two bins (thousands of same-address atomics otherwise)
         auto vote = [&](uint32_t key) {
-            if (key != kNoKey && (key & hi_mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1);
+            const uint32_t bin = (key != kNoKey && (key & hi_mask) == prefix) ? ((key >> shift) & 255u) : 256u;
+            const unsigned same = __match_any_sync(PR_FULL_MASK, bin);
+            if (bin < 256u && lane == __ffs(same) - 1) atomicAdd(&s_hist[bin], __popc(same));
         };
 #pragma unroll
         for (int r = 0; r < kHeadRegs; ++r) vote(hk[r]);
-        for (int c = (int)threadIdx.x + kHeadRegs * kWideWarps * 32; c < C; c += kWideWarps * 32) vote(head_key(c));
+        for (int c0 = kHeadRegs * kWideWarps * 32; c0 < C; c0 += kWideWarps * 32) {   // (warp-uniform trip count)
+            const int c = c0 + (int)threadIdx.x;
+            vote(c < C ? head_key(c) : kNoKey);
+        }
         __syncthreads();
         if (warp == 0) {   // lane l holds bins 255 - 8 l ... 248 - 8 l: the bin in which the running count from the top reaches `remaining`
             int cnt[8], sum = 0;

@@ -29,6 +29,9 @@
 
 #include "bm25_hot.cuh"
 
+#ifndef PR_LEAN_FOLD
+#define PR_LEAN_FOLD 6  // bit v: kernel variant v folds the END of a sub-tile into its last step
+#endif
 #ifndef PR_LEAN_PIPE
 #define PR_LEAN_PIPE 2
 #endif
@@ -169,6 +172,9 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
 {
     constexpr bool REFRESH = VAR == 1;
     constexpr int kEpochs = VAR == 2 ? 4 : 2;
+    // the END of a sub-tile folded into its last step (see finish_list) -- not in variant 0, the one that runs while the
+    // bounds are weak: with most sub-tiles scanned the folded layout measured 2-4% slower per launch, 3% faster otherwise
+    constexpr bool kFold = (PR_LEAN_FOLD >> VAR) & 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -489,7 +495,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                 // ---- no-ops up to a multiple of kPipe; the END sits in the last ring slot
                 int len = chunk;
                 uint32_t fold = 0u;
-                if (end && len > 0 && len % kPipe == 0) {
+                if (kFold && end && len > 0 && len % kPipe == 0) {
                     fold = (uint32_t)kFlagEnd | ((uint32_t)g << kSubIdxShift);
                 } else {
                     const int pad = (kPipe - ((len + (end ? 1 : 0)) % kPipe)) % kPipe;
@@ -588,7 +594,8 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                     prev_e = e;
                     if (ss == 0) t0 = t;
                     if (t > 0) {
-                        const int total = (t + kPipe - 1) / kPipe * kPipe;  // t steps rounded up to whole rings; the END rides on the last slot
+                        // t steps rounded up to whole rings, the END riding on the last slot (or, unfolded, a step of its own)
+                        const int total = (t + (kFold ? kPipe - 1 : kPipe)) / kPipe * kPipe;
                         if (base + total > kListCap) {
                             chunked = ss == 0;
                             break;
@@ -632,7 +639,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                 if (s == 0) write_steps(tl + pre + max(0, w0 - pre) - w0, max(0, w0 - pre), min(n, w0 + chunk - pre), n_wide);
                 int len = chunk;
                 uint32_t fold = 0u;
-                if (fin && len > 0 && len % kPipe == 0) {
+                if (kFold && fin && len > 0 && len % kPipe == 0) {
                     fold = (uint32_t)kFlagEnd | ((uint32_t)g0 << kSubIdxShift);
                 } else {
                     const int pad = (kPipe - ((len + (fin ? 1 : 0)) % kPipe)) % kPipe;

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--k", default="10", help="comma list of depths")
     ap.add_argument("--kind", default="round0", help="round0 (question-sized queries) or later (LM-transcript-sized, 64..1024 terms)")
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--graph", action="store_true", help="also time the calls replayed from a CUDA graph")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     bs = [int(x) for x in args.batches.split(",")]
@@ -49,8 +50,30 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / (reps * n_calls)
         n_terms = float(qi[n_calls] if b == 1 else qi[b]) / (n_calls if b == 1 else b)
-        print(json.dumps({"batch": b, "k": k, "kind": args.kind, "terms_per_query": n_terms, "ms_per_call": ms, "qps": b / ms * 1e3,
-                          "launches": gi.last_launches, "distinct_calls_averaged": n_calls}), flush=True)
+        row = {"batch": b, "k": k, "kind": args.kind, "terms_per_query": n_terms, "ms_per_call": ms, "qps": b / ms * 1e3,
+               "launches": gi.last_launches, "distinct_calls_averaged": n_calls}
+        if args.graph and b <= 512:
+            # the same calls captured once in a CUDA graph and replayed: the device time of a call without the host's
+            # per-call work (Python argument checks + ctypes + three kernel launches, which exceed the device time of
+            # a single query)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(graph, stream=side):
+                    outs = [gi.topk(d_qi, d_qt, k, check_status=False) for d_qi, d_qt in calls]
+                graph.replay()
+                side.synchronize()
+                want = [gi.topk(d_qi, d_qt, k) for d_qi, d_qt in calls]
+                side.synchronize()
+                assert all(torch.equal(o[0], w[0]) and torch.equal(o[1], w[1]) for o, w in zip(outs, want)), "graph replay differs"
+                e0.record(side)
+                for _ in range(reps):
+                    graph.replay()
+                e1.record(side)
+                side.synchronize()
+            row["ms_per_call_graph_replay"] = e0.elapsed_time(e1) / (reps * n_calls)
+        print(json.dumps(row), flush=True)
 
 
 if __name__ == "__main__":

@@ -305,6 +305,8 @@ def main():
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "allreduce", "none"],
                     help="N > 1: how the shards share score bounds (p2p = live over NVLink peer memory)")
+    ap.add_argument("--list-rounds", type=int, default=4,
+                    help="N > 1, p2p: launches of a call behind which the shards' running lists are all-gathered (union bound)")
     ap.add_argument("--tune", default="", help="comma list key=value for pr_bm25_tuning_t")
     args = ap.parse_args()
 
@@ -368,7 +370,7 @@ def main():
             # all-reduce form of the same exchange (every rank takes the same branch: the failure is collective)
             ok = torch.ones(1, device=device)
             try:
-                sharded = ShardedBM25(gi, exchange="p2p", max_queries=nq)
+                sharded = ShardedBM25(gi, exchange="p2p", max_queries=nq, list_rounds=args.list_rounds)
             except Exception as ex:
                 log(f"[bench] rank {rank}: peer-memory thresholds unavailable ({ex!r})")
                 ok.zero_()
@@ -509,7 +511,8 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": make_config(args, world, nnz_total),
         "plan": {"tuning": gi.get_tuning(), "scoring_launches_per_step": n_score_launches, "nnz_shard0": gi.nnz,
-                 "threshold_exchange": exchange_used},
+                 "threshold_exchange": exchange_used,
+                 "union_bound_rounds": sharded.list_rounds if sharded is not None else 0},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e / args.steps},

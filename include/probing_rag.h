@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PR_VERSION 200 /* 0.2.0 */
+#define PR_VERSION 201 /* 0.2.0 */
 
 #define PR_OK 0
 #define PR_EINVAL (-1)     /* bad argument (null pointer, k out of range, misaligned buffer) */
@@ -135,6 +135,17 @@ int pr_bm25_topk_range(pr_index_t *index, int32_t n_queries, const int64_t *q_in
                        const int32_t *q_terms_dev, int64_t n_q_terms, int32_t k, float *out_scores_dev,
                        int32_t *out_doc_ids_dev, void *workspace_dev, size_t workspace_bytes,
                        int32_t launch_begin, int32_t launch_end, pr_stream_t stream);
+
+/* A stronger exchange for the first launches of a large batch, while bounds are still weak: the K-th largest score of
+ * the UNION of all shards' running lists (the shards hold disjoint documents, so K documents scoring at least that
+ * exist) instead of the best of the shards' own K-th scores.  Between two ranges the workspace holds, at byte offset
+ * pr_bm25_running_scores_offset(), float run_scores[n_queries][k]: this shard's best k scores so far, descending,
+ * -1 = empty slot.  The caller all-gathers those arrays ([n_lists][n_queries][k]) and hands them to
+ * pr_bm25_raise_union_bound, which raises every query's bound to the k-th largest of its n_lists * k scores --
+ * in the workspace or, with peers set, in this rank's peer-shared array (all ranks compute the same value). */
+size_t pr_bm25_running_scores_offset(const pr_index_t *index, int32_t n_queries, int32_t k);
+int pr_bm25_raise_union_bound(pr_index_t *index, int32_t n_queries, int32_t k, const float *gathered_scores_dev,
+                              int32_t n_lists, void *workspace_dev, size_t workspace_bytes, pr_stream_t stream);
 
 /* Thresholds shared LIVE between the GPUs of a doc-sharded corpus (one process per GPU, NVLink / NVSwitch peer
  * memory) -- the fused form of the exchange above: every rank keeps float theta[2][capacity] in memory its peers can

@@ -55,6 +55,8 @@ SIGNATURES = {
     "pr_bm25_topk": (ctypes.c_int, [c_vp, c_i32, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "pr_bm25_num_launches": (c_i32, [c_vp, c_i32, c_i32, c_i64]),
     "pr_bm25_theta_offset": (c_sz, [c_vp, c_i32, c_i32]),
+    "pr_bm25_running_scores_offset": (c_sz, [c_vp, c_i32, c_i32]),
+    "pr_bm25_raise_union_bound": (ctypes.c_int, [c_vp, c_i32, c_i32, c_vp, c_i32, c_vp, c_sz, c_vp]),
     "pr_bm25_topk_range": (ctypes.c_int, [c_vp, c_i32, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_sz, c_i32, c_i32,
                                           c_vp]),
     "pr_peer_alloc": (ctypes.c_int, [ctypes.c_int, c_sz, ctypes.POINTER(c_vp), ctypes.c_char_p]),

@@ -300,6 +300,42 @@ __global__ void __launch_bounds__(kWideWarps * 32) bm25_merge_wide_kernel(
     }
 }
 
+// K-th largest of the union of n_lists descending score lists per query (pr_bm25_raise_union_bound): one warp per
+// query folds them through a register list; positions stand in for document ids (the lists hold distinct documents).
+template <int E>
+__global__ void __launch_bounds__(128) bm25_union_bound_kernel(const float *__restrict__ gs, int n_lists, int B, int K, float *theta)
+{
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= B) return;
+    WarpTopK<E> L;
+    L.reset();
+    float ks = PR_SENT_SCORE;
+    int kd = PR_SENT_DOC;
+    for (int g = 0; g < n_lists; ++g) {
+        const float *ps = gs + ((size_t)g * B + q) * K;
+        bool done = false;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int i0 = e * 32;
+            if (done || i0 >= K) break;
+            const float es = i0 + lane < K ? ps[i0 + lane] : -1.f;
+            const int n = min(32, K - i0);
+            for (int i = 0; i < n; ++i) {
+                const float bs = __shfl_sync(PR_FULL_MASK, es, i);
+                const int bd = g * K + i0 + i;
+                if (bs < 0.f || !pr_beats(bs, bd, ks, kd)) {   // empty slot / sorted: the rest of this list loses too
+                    done = true;
+                    break;
+                }
+                L.insert(bs, bd, lane);
+                L.kth(K, ks, kd);
+            }
+        }
+    }
+    if (ks > 0.f) prw::raise_theta(theta, nullptr, 0, q, ks, lane);
+}
+
 // Workspace initialisation.  (The query CSR is validated by the scoring warps, item by item: bm25_lean.cuh.)
 __global__ void bm25_init_kernel(float *run_s, int32_t *run_d, float *theta, int64_t n_run, int B, int32_t *counters,
                                  int n_counters, int32_t *status)
@@ -890,6 +926,44 @@ extern "C" size_t pr_bm25_theta_offset(const pr_index_t *index, int32_t n_querie
 {
     if (!index || n_queries < 0 || k < 1 || k > PR_MAX_K) return 0;
     return make_layout(index, n_queries, k).off_theta;
+}
+
+extern "C" size_t pr_bm25_running_scores_offset(const pr_index_t *index, int32_t n_queries, int32_t k)
+{
+    if (!index || n_queries < 0 || k < 1 || k > PR_MAX_K) return 0;
+    return make_layout(index, n_queries, k).off_run_s;
+}
+
+extern "C" int pr_bm25_raise_union_bound(pr_index_t *index, int32_t n_queries, int32_t k, const float *gathered_scores_dev,
+                                         int32_t n_lists, void *workspace_dev, size_t workspace_bytes, pr_stream_t stream)
+{
+    if (!index || n_queries < 0 || k < 1 || k > PR_MAX_K || n_lists < 1 || !gathered_scores_dev || !workspace_dev) {
+        pr_set_error("pr_bm25_raise_union_bound: bad argument");
+        return PR_EINVAL;
+    }
+    const Layout l = make_layout(index, n_queries, k);
+    if (workspace_bytes < l.total) {
+        pr_set_error("pr_bm25_raise_union_bound: workspace of %zu bytes, need %zu", workspace_bytes, l.total);
+        return PR_EWORKSPACE;
+    }
+    if (n_queries == 0) return PR_OK;
+    float *theta = (float *)((unsigned char *)workspace_dev + l.off_theta);
+    if (index->peer_local) {   // the half of the peer-shared array the running call uses
+        if (n_queries > index->peer_capacity) {
+            pr_set_error("pr_bm25_raise_union_bound: %d queries, the peer threshold arrays hold %lld", n_queries, (long long)index->peer_capacity);
+            return PR_EINVAL;
+        }
+        theta = index->peer_local + (size_t)(index->peer_calls & 1) * index->peer_capacity;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((n_queries + 3) / 4);
+    switch (e_of(k)) {
+    case 1: bm25_union_bound_kernel<1><<<grid, 128, 0, st>>>(gathered_scores_dev, n_lists, n_queries, k, theta); break;
+    case 2: bm25_union_bound_kernel<2><<<grid, 128, 0, st>>>(gathered_scores_dev, n_lists, n_queries, k, theta); break;
+    default: bm25_union_bound_kernel<4><<<grid, 128, 0, st>>>(gathered_scores_dev, n_lists, n_queries, k, theta); break;
+    }
+    PR_CUDA_CHECK(cudaGetLastError());
+    return PR_OK;
 }
 
 extern "C" int64_t pr_bm25_last_launches(const pr_index_t *index) { return index ? index->last_launches : 0; }

@@ -279,7 +279,7 @@ class BM25Index:
         return q_indptr.contiguous(), q_terms.contiguous(), nq, out
 
     def topk(self, q_indptr: torch.Tensor, q_terms: torch.Tensor, k: int, out=None, check_status=True,
-             exchange=None, exchange_rounds: int | None = None):
+             exchange=None, exchange_rounds: int | None = None, list_exchange=None, list_rounds: int = 0):
         """Device CSR query batch -> (scores f32[B,k], doc_ids i32[B,k]) on the device.
         Enqueues on the current stream; with check_status the stream is synchronised and a bad
         term id / inconsistent CSR raises ValueError like bm25s does (App. A.5).
@@ -287,7 +287,12 @@ class BM25Index:
         exchange: optional callable(theta f32[B]) run between the launches of the call (doc-range
         shards: an all-reduce(MAX) of the per-query k-th-score bounds over the ranks).
         Every rank must join the same number of exchanges: `exchange_rounds` (>= this shard's launches - 1)
-        is what the longest shard needs, see `ShardedBM25`."""
+        is what the longest shard needs, see `ShardedBM25`.
+
+        list_exchange: optional callable(run_scores f32[B,k]) -> gathered f32[G,B,k], run after each of the first
+        `list_rounds` launches (all of them on every rank, also on a shard with fewer launches): the all-gather of
+        the shards' running score lists; every query's bound is then raised to the k-th largest score of the union
+        (pr_bm25_raise_union_bound).  Works with private and with peer-shared thresholds."""
         q_indptr, q_terms, nq, out = self._check_query_batch(q_indptr, q_terms, k, out)
         if nq == 0:
             return out
@@ -297,8 +302,27 @@ class BM25Index:
         args = (self._handle, nq, q_indptr.data_ptr(), q_terms.data_ptr() if q_terms.numel() else None, q_terms.numel(), k,
                 out[0].data_ptr(), out[1].data_ptr(), ws.data_ptr(), ws.numel())
         with torch.cuda.device(self.device):
-            if exchange is None or nq == 0:
+            if exchange is None and (list_exchange is None or list_rounds < 1):
                 _lib.check(L.pr_bm25_topk(*args, stream))
+            elif exchange is None:
+                n_launch = int(L.pr_bm25_num_launches(self._handle, nq, k, -1))
+                off = int(L.pr_bm25_running_scores_offset(self._handle, nq, k))
+                run_s = ws[off:off + 4 * nq * k].view(torch.float32).view(nq, k)
+                li = done = 0
+                while li < n_launch:
+                    if done < list_rounds:
+                        _lib.check(L.pr_bm25_topk_range(*args, li, li + 1, stream))
+                        li += 1
+                        gathered = list_exchange(run_s)
+                        done += 1
+                        if li < n_launch:             # (behind the call's last launch there is nothing left to filter)
+                            _lib.check(L.pr_bm25_raise_union_bound(self._handle, nq, k, gathered.data_ptr(), gathered.shape[0],
+                                                                   ws.data_ptr(), ws.numel(), stream))
+                    else:                             # the launches behind the exchanged ones go out as one range
+                        _lib.check(L.pr_bm25_topk_range(*args, li, n_launch, stream))
+                        li = n_launch
+                for _ in range(list_rounds - done):   # a shard with fewer launches still joins the rounds the others run
+                    list_exchange(run_s)
             else:
                 n_launch = int(L.pr_bm25_num_launches(self._handle, nq, k, -1))
                 off = int(L.pr_bm25_theta_offset(self._handle, nq, k))

@@ -140,12 +140,17 @@ class ShardedBM25:
     doc_id_base = 0          # the merged lists carry global doc ids
 
     def __init__(self, index=None, group=None, local_topk: Callable | None = None,
-                 merge: Callable | None = None, exchange="allreduce", max_queries: int = 65536):
+                 merge: Callable | None = None, exchange="allreduce", max_queries: int = 65536, list_rounds: int = 4):
         """exchange: how the shards tell each other their score bounds while a call runs --
         "p2p": raised live in each other's memory by the scoring warps (NVLink peer memory, `PeerThresholds`;
                batches of up to `max_queries` queries);
         "allreduce" (or True): an all-reduce(MAX) between the launches of the call;
-        None / False: not at all (every shard filters with what it found itself)."""
+        None / False: not at all (every shard filters with what it found itself).
+        list_rounds: with "p2p", behind each of the first `list_rounds` launches of a call (the ramp of a large
+               batch, while bounds are weak and most tiles are still scanned) the shards' running score lists are
+               all-gathered and every bound raised to the k-th largest score of the UNION -- stronger than the best
+               single shard's k-th score that the live exchange carries.  0 = never; calls of one launch (small
+               batches) never exchange."""
         if index is None and local_topk is None:
             raise ValueError("pass the shard's BM25Index or a local_topk callable")
         if exchange is True:
@@ -161,8 +166,10 @@ class ShardedBM25:
         self.exchange = exchange if (real and exchange) else None
         self._exchange = self.exchange == "allreduce"
         self._peers = PeerThresholds(index, max_queries, group) if self.exchange == "p2p" else None
+        self.list_rounds = int(list_rounds) if self.exchange == "p2p" else 0
+        self._run_gath = {}
         self._max_docs = None
-        if self._exchange:
+        if self._exchange or self.list_rounds > 0:
             # every rank must join the same number of all-reduces per call: as many as the LONGEST shard has launches
             n = torch.tensor([index.n_docs], dtype=torch.int64, device=index.device)
             dist.all_reduce(n, op=dist.ReduceOp.MAX, group=group)
@@ -183,10 +190,29 @@ class ShardedBM25:
         if self._local is not None:
             return self._local(q_indptr, q_terms, k)
         if not self._exchange:
+            nq = q_indptr.numel() - 1
+            if self.list_rounds > 0 and nq > 0:
+                # every rank must run the same number of all-gathers: decided from the LONGEST shard's launch plan
+                rounds = min(self.list_rounds, self.index.num_launches(nq, k, n_docs=self._max_docs) - 1)
+                if rounds > 0:
+                    return self.index.topk(q_indptr, q_terms, k, check_status=False, list_exchange=self._gather_running,
+                                           list_rounds=rounds)
             return self.index.topk(q_indptr, q_terms, k, check_status=False)
         rounds = self.index.num_launches(q_indptr.numel() - 1, k, n_docs=self._max_docs) - 1
         return self.index.topk(q_indptr, q_terms, k, check_status=False,
                                exchange=lambda theta: exchange_thresholds(theta, self.group), exchange_rounds=rounds)
+
+    def _gather_running(self, run_s: torch.Tensor) -> torch.Tensor:
+        """[B,k] running scores of this shard -> [G,B,k] of all shards (one all-gather, buffer reused)."""
+        world = _world(self.group)
+        key = tuple(run_s.shape)
+        buf = self._run_gath.get(key)
+        if buf is None:
+            if len(self._run_gath) > 16:
+                self._run_gath.clear()
+            buf = self._run_gath[key] = torch.empty((world,) + key, dtype=torch.float32, device=run_s.device)
+        dist.all_gather_into_tensor(buf.view(world * key[0], key[1]), run_s, group=self.group)
+        return buf
 
     def topk(self, q_indptr, q_terms, k: int, check_status: bool = True):
         s, d = self._local_topk(q_indptr, q_terms, k)

@@ -27,12 +27,13 @@ def test_library_builds_and_exports_all_declared_symbols():
 
 def test_version_and_argument_errors_without_gpu():
     L = _lib.lib()
-    assert L.pr_version() == 200
+    assert L.pr_version() == 201
     # argument validation happens before any CUDA call
     assert L.pr_topk_merge(4, 0, 2, None, None, None, None, None) == _lib.PR_EINVAL
     assert b"bad argument" in L.pr_last_error() or b"k must be" in L.pr_last_error()
     assert L.pr_bm25_workspace_bytes(None, 4, 10) == 0
     assert L.pr_bm25_num_launches(None, 4, 10, -1) == -1 and L.pr_bm25_theta_offset(None, 4, 10) == 0
+    assert L.pr_bm25_running_scores_offset(None, 4, 10) == 0
     h = ctypes.c_void_p()
     assert L.pr_index_create(ctypes.byref(h), 0, 10, 0, 10, 4, 0, None, None, None) == _lib.PR_EINVAL
 

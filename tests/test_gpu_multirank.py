@@ -46,11 +46,12 @@ def _worker(rank, world, port, out_dir):
         gi.set_tuning(subs_per_item=2, docs_per_launch=16384, min_items=1, items_per_warp=1)
         d_qi, d_qt = torch.from_numpy(qi).to(dev), torch.from_numpy(qt).to(dev)
         res = {}
-        for name, mode in (("p2p", "p2p"), ("exchange", "allreduce"), ("plain", None), ("p2p_again", "p2p")):
-            if name == "p2p_again":   # ... this time with the kernel variant a 65,536-query batch runs
-                gi.set_tuning(batch_variant=2)
-            sb = ShardedBM25(gi, exchange=mode, max_queries=NQ)
-            assert sb.exchange == mode
+        for name, mode, list_rounds in (("p2p", "p2p", 4), ("p2p_live_only", "p2p", 0), ("exchange", "allreduce", 0),
+                                        ("plain", None, 0), ("p2p_again", "p2p", 100)):
+            if name == "p2p_again":   # ... this time with the kernel variant a 65,536-query batch runs, and a union
+                gi.set_tuning(batch_variant=2)      # bound behind every launch
+            sb = ShardedBM25(gi, exchange=mode, max_queries=NQ, list_rounds=list_rounds)
+            assert sb.exchange == mode and sb.list_rounds == (list_rounds if mode == "p2p" else 0)
             for k in (10, 100, 10):                 # an odd number of calls: the next p2p instance starts on the other parity
                 s, d = sb.topk(d_qi, d_qt, k)
                 hs, hd, h2d, d2h = sb.topk_host(qi, qt, k)
@@ -105,6 +106,6 @@ def test_nccl_doc_shards_equal_single_index_and_oracle(tmp_path, world):
         for r in range(world):
             got = np.load(tmp_path / f"r{r}.npz")
             assert int(got["launches"][0]) > 2
-            for name in ("p2p", "exchange", "plain", "p2p_again"):
+            for name in ("p2p", "p2p_live_only", "exchange", "plain", "p2p_again"):
                 assert np.array_equal(got[f"{name}_d{k}"], od), f"rank {r} {name}: merged doc ids differ (k={k})"
                 assert np.array_equal(got[f"{name}_s{k}"], os_), f"rank {r} {name}: merged scores differ (k={k})"

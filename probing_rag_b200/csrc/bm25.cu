@@ -963,6 +963,7 @@ extern "C" int pr_bm25_raise_union_bound(pr_index_t *index, int32_t n_queries, i
     default: bm25_union_bound_kernel<4><<<grid, 128, 0, st>>>(gathered_scores_dev, n_lists, n_queries, k, theta); break;
     }
     PR_CUDA_CHECK(cudaGetLastError());
+    index->last_launches += 1;
     return PR_OK;
 }
 

@@ -392,6 +392,56 @@ def test_threshold_exchange_between_shards_keeps_the_merged_lists_bit_identical(
         assert_parity(ms.cpu().numpy(), md.cpu().numpy(), ref_s, ref_d)
 
 
+@pytest.mark.parametrize("g", [2, 4])
+def test_union_bound_exchange_between_shards_keeps_the_merged_lists_bit_identical(small_corpus, g):
+    """The stronger exchange of the first launches (pr_bm25_raise_union_bound), in lock step on one GPU: behind every
+    launch the shards' running score lists are stacked (the all-gather) and every shard's bound is raised to the
+    k-th largest score of the union.  The bound must be exactly that value where it beats the shard's own, and the
+    merged lists must still equal the single index bit for bit."""
+    from probing_rag_b200 import _lib, merge_topk
+    qi, qt = small_corpus["q_indptr"][:301], small_corpus["q_terms"]
+    nq = len(qi) - 1
+    L = _lib.lib()
+    for k in (10, 40):
+        ref_s, ref_d = co.retrieve_batch(small_corpus["index"], qi, qt, k, n_threads=8)
+        shards = build_shards(small_corpus, g)
+        outs, calls, thetas, runs = [], [], [], []
+        for gi in shards:
+            tune(gi, docs_per_launch=16384, min_items=1, subs_per_item=4)
+            d_qi, d_qt = to_dev(gi, qi, qt)
+            out = (torch.empty((nq, k), dtype=torch.float32, device=gi.device), torch.empty((nq, k), dtype=torch.int32, device=gi.device))
+            ws = gi._workspace(nq, k)
+            off = int(L.pr_bm25_theta_offset(gi._handle, nq, k))
+            thetas.append(ws[off:off + 4 * nq].view(torch.float32))
+            off = int(L.pr_bm25_running_scores_offset(gi._handle, nq, k))
+            runs.append(ws[off:off + 4 * nq * k].view(torch.float32).view(nq, k))
+            calls.append((gi, (gi._handle, nq, d_qi.data_ptr(), d_qt.data_ptr(), d_qt.numel(), k, out[0].data_ptr(), out[1].data_ptr(),
+                               ws.data_ptr(), ws.numel()), (d_qi, d_qt), ws))
+            outs.append(out)
+        n_launch = {gi.num_launches(nq, k) for gi in shards}
+        assert len(n_launch) == 1 and min(n_launch) > 2
+        stream = torch.cuda.current_stream().cuda_stream
+        raised = 0
+        for li in range(min(n_launch)):
+            for gi, args, _, _ in calls:
+                _lib.check(L.pr_bm25_topk_range(*args, li, li + 1, stream))
+            if li + 1 == min(n_launch):
+                break
+            gathered = torch.stack(runs).contiguous()                       # [G, B, k]
+            union_kth = gathered.permute(1, 0, 2).reshape(nq, -1).topk(k, dim=1).values[:, k - 1]
+            before = [t.clone() for t in thetas]
+            for gi, args, _, ws in calls:
+                _lib.check(L.pr_bm25_raise_union_bound(gi._handle, nq, k, gathered.data_ptr(), g, ws.data_ptr(), ws.numel(), stream))
+            for t, b in zip(thetas, before):
+                want = torch.where(union_kth > 0, torch.maximum(b, union_kth), b)
+                assert torch.equal(t, want)
+                raised += int((t > b).sum())
+        assert raised > 0
+        ms, md = merge_topk(torch.stack([o[0] for o in outs]), torch.stack([o[1] for o in outs]))
+        torch.cuda.synchronize()
+        assert_parity(ms.cpu().numpy(), md.cpu().numpy(), ref_s, ref_d)
+
+
 def test_gpu_index_builder_bit_exact(small_corpus):
     """BM25Index.from_tokens on the device == the oracle's builder (weights bit for bit)."""
     from probing_rag_b200 import BM25Index

@@ -16,7 +16,7 @@ echo "== ncu full: prober GEMMs"; timeout 900 ncu --set full --clock-control non
 fi
 if [ $T = all ] || [ $T = sweep ]; then
 echo "== config 5 sweep"; rm -f gpurun_out/r2e_config5_sweep.jsonl
-timeout 900 python tools/latency.py --batches 1,8,64,512,4096,65536 --k 1,5,10,50,100 --reps 10 2>/dev/null >> gpurun_out/r2e_config5_sweep.jsonl
+timeout 900 python tools/latency.py --batches 1,8,64,512,4096,65536 --k 1,5,10,50,100 --reps 10 --graph 2>/dev/null >> gpurun_out/r2e_config5_sweep.jsonl
 timeout 900 python tools/latency.py --batches 1,8,64,512,4096 --k 1,10,100 --reps 3 --kind later 2>/dev/null >> gpurun_out/r2e_config5_sweep.jsonl
 wc -l gpurun_out/r2e_config5_sweep.jsonl
 echo "== prober bench"; timeout 300 python tools/bench_prober.py --rows 16384 --with-bm25 --out gpurun_out/r2e_prober_bench_16k.json 2>&1 | tail -n 1 | cut -c1-300

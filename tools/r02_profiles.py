@@ -123,7 +123,9 @@ def config5():
     shutil.copy(os.path.join(G, "r2e_config5_sweep.jsonl"), os.path.join(OUT, "config5_sweep.jsonl"))
     md = ["# BASELINE config 5: batch x depth x retrieval round (21,015,324 passages, 1xB200, device time per call)", "",
           "`tools/latency.py` on the full-size index; round 0 = question-sized queries (~6 terms), rounds 1-3 = the decoded",
-          "transcript as the query (`exp_rag.py:428`, 64..1024 terms, ~350 on average).  ms per `pr_bm25_topk` call (queries/s).", ""]
+          "transcript as the query (`exp_rag.py:428`, 64..1024 terms, ~350 on average).  ms per `pr_bm25_topk` call (queries/s);",
+          "batch 1 = the mean over 64 DIFFERENT single queries, one call each (a single query's time is that of its terms'",
+          "posting lists).  In brackets where measured: the same calls replayed from a CUDA graph (no per-call host work).", ""]
     for kind, title in (("round0", "round 0"), ("later", "rounds 1-3 (transcript-sized queries)")):
         sel = [r for r in rows if r["kind"] == kind]
         ks = sorted({r["k"] for r in sel})
@@ -133,7 +135,8 @@ def config5():
             cells = []
             for k in ks:
                 r = next((r for r in sel if r["batch"] == b and r["k"] == k), None)
-                cells.append(f"{r['ms_per_call']:.3f} ms ({r['qps']:,.0f}/s)" if r else "")
+                g = f" [{r['ms_per_call_graph_replay']:.3f}]" if r and "ms_per_call_graph_replay" in r else ""
+                cells.append(f"{r['ms_per_call']:.3f} ms ({r['qps']:,.0f}/s){g}" if r else "")
             md.append(f"| {b} | " + " | ".join(cells) + " |")
         md.append("")
     open(os.path.join(OUT, "config5_sweep.md"), "w").write("\n".join(md))

@@ -446,6 +446,7 @@ struct pr_index {
     int32_t n_peers;
     int64_t peer_capacity;
     uint64_t peer_calls;
+    int union_lists;   // shards behind the last union bound of the running call (1 = none): see the variant choice per launch
 };
 
 namespace {
@@ -630,6 +631,7 @@ extern "C" int pr_index_create(pr_index_t **out, int device, int64_t n_docs_glob
     ix->n_peers = 0;
     ix->peer_capacity = 0;
     ix->peer_calls = 0;
+    ix->union_lists = 1;
     ix->device = device;
     ix->n_docs_global = n_docs_global;
     ix->doc_id_base = doc_id_base;
@@ -964,6 +966,7 @@ extern "C" int pr_bm25_raise_union_bound(pr_index_t *index, int32_t n_queries, i
     }
     PR_CUDA_CHECK(cudaGetLastError());
     index->last_launches += 1;
+    index->union_lists = n_lists;
     return PR_OK;
 }
 
@@ -1004,6 +1007,7 @@ extern "C" int pr_bm25_topk_range(pr_index_t *index, int32_t n_queries, const in
     if (launch_begin == 0) {
         index->last_launches = 0;
         index->ev_used = 0;
+        index->union_lists = 1;
     }
     cudaStream_t st = (cudaStream_t)stream;
     unsigned char *ws = (unsigned char *)workspace_dev;
@@ -1113,7 +1117,10 @@ extern "C" int pr_bm25_topk_range(pr_index_t *index, int32_t n_queries, const in
     for (int li = launch_begin; li < launch_end; ++li) {
         const int chunk0 = l.launch_chunk0[li], Cl = l.launch_chunks[li];
         const int64_t items = (int64_t)n_queries * Cl;
-        const int late = li > first_full && l.L > 1 ? 1 : 0;
+        // ... or, on a doc-range shard, once the union bound (pr_bm25_raise_union_bound) stands for enough documents
+        // over all shards that scans are rare (a sub-tile is scanned with probability ~2048 k / documents seen)
+        const int64_t seen = (int64_t)chunk0 * l.G * prw::kSub * index->union_lists;
+        const int late = l.L > 1 && (li > first_full || (index->union_lists > 1 && seen >= (int64_t)81920 * k)) ? 1 : 0;
         const score_fn_t fn = fns[late];
         int64_t grid = (int64_t)occs[late] * index->num_sms;
         const int64_t need = (items + nw - 1) / nw;

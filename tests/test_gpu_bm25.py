@@ -407,7 +407,7 @@ def test_union_bound_exchange_between_shards_keeps_the_merged_lists_bit_identica
         shards = build_shards(small_corpus, g)
         outs, calls, thetas, runs = [], [], [], []
         for gi in shards:
-            tune(gi, docs_per_launch=16384, min_items=1, subs_per_item=4)
+            tune(gi, subs_per_item=2, docs_per_launch=4096, min_items=1, items_per_warp=1)
             d_qi, d_qt = to_dev(gi, qi, qt)
             out = (torch.empty((nq, k), dtype=torch.float32, device=gi.device), torch.empty((nq, k), dtype=torch.int32, device=gi.device))
             ws = gi._workspace(nq, k)

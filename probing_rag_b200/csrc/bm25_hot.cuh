@@ -16,9 +16,9 @@
 //     group, in a bank the group's postings leave free -- so there are no
 //     validity masks and no alignment heads; a remainder of more than 32 postings takes one
 //     padded wide step rather than up to three narrow ones (fewer steps beat fewer slots: +10%);
-//   * inside a segment the postings are dealt round-robin over the steps' 32-slot groups in
-//     bank-sorted order (doc % 32), so the 32 documents a warp touches together fall into
-//     distinct banks whenever the segment's bank histogram allows it.
+//   * inside a segment the postings are placed bank-aware (bank = doc % 32): most 32-slot groups are CLEAN -- one
+//     posting per bank, never a conflict -- and the few last groups absorb what the banks hold beyond that
+//     (hot_fill_kernel).
 //
 // The order of a term's postings inside a sub-tile is irrelevant for the sums (a document occurs
 // once per term), so scores stay bit-identical.  Everything is built on the device by
@@ -160,6 +160,7 @@ static __global__ void __launch_bounds__(256) hot_fill_kernel(const int64_t *ind
                                                        int n_sub, int64_t n_seg, const uint32_t *hot_off, unsigned char *stream)
 {
     __shared__ int s_fill[8][32];
+    __shared__ int s_dirty0[8][32];
     __shared__ unsigned s_banks[8][kMaxGroups];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int *fill = s_fill[w];
@@ -184,48 +185,82 @@ static __global__ void __launch_bounds__(256) hot_fill_kernel(const int64_t *ind
                 ww = ow + 1;
             }
         };
-        // ---- bank histogram -> start of every bank in bank-sorted order
+        // ---- bank histogram (bank = tile word index mod 32 = doc % 32)
         const int64_t p0 = indptr[row_term[row]] + sb;
         fill[lane] = 0;
         for (int i = lane; i < groups; i += 32) banks[i] = 0u;
         __syncwarp();
         for (int i = lane; i < n; i += 32) atomicAdd(&fill[doc_ids[p0 + i] & 31], 1);
         __syncwarp();
-        const int c = fill[lane];
-        int incl = c;
+        const int c = fill[lane];  // postings in bank `lane`
+        // ---- CLEAN and DIRTY groups.  A group (the 32 slots one LDS/STS of the scoring kernel touches) costs as many
+        // shared-memory wavefronts as its fullest bank holds postings.  n ~ 32 x groups leaves no slack: half of the banks
+        // hold more postings than there are groups, and dealing the postings round-robin put one of those extras into
+        // nearly every group (measured: 1.75 wavefronts per wide-step LDS/STS).  Instead the first C groups are CLEAN --
+        // group g takes the g-th posting of every bank that has one, into lane = bank, so it never conflicts -- and what
+        // the banks have beyond C postings goes round-robin into the last D = groups - C DIRTY groups, which absorb all
+        // the imbalance.  C = the largest count for which the leftovers fit: 32 D >= sum_b max(0, c_b - C).
+        int C = groups, R = 0;
+#pragma unroll 1
+        for (; C >= 0; --C) {
+            int r = max(0, c - C);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(PR_FULL_MASK, r, o);
+            R = r;
+            if (32 * (groups - C) >= r) break;
+        }
+        const int D = groups - C;
+        const int left = max(0, c - C);  // this bank's postings in the dirty groups
+        int incl = left;
         for (int o = 1; o < 32; o <<= 1) {
             const int v = __shfl_up_sync(PR_FULL_MASK, incl, o);
             if (lane >= o) incl += v;
         }
         __syncwarp();
-        fill[lane] = incl - c;
+        fill[lane] = 0;                      // running count per bank
+        s_dirty0[w][lane] = incl - left;     // first dirty rank of this bank
         __syncwarp();
-        // ---- deal: the i-th posting in bank order goes to group i % groups, lane i / groups, so a bank's postings
-        // land in different groups (as long as it has no more than `groups` of them)
         for (int i = lane; i < n; i += 32) {
             const int d = doc_ids[p0 + i];
             const float wt = weights[p0 + i];
-            const int rank = atomicAdd(&fill[d & 31], 1);
-            const int grp = rank % groups, ln = rank / groups;
+            const int b = d & 31;
+            const int k = atomicAdd(&fill[b], 1);
+            int grp, ln;
+            if (k < C) {
+                grp = k;
+                ln = b;
+            } else {
+                const int j = s_dirty0[w][b] + (k - C);
+                grp = C + j % D;
+                ln = j / D;
+                atomicOr(&banks[grp], 1u << b);
+            }
             int ow, ww;
             slot_words(grp, ln, ow, ww);
             out[ow] = (uint32_t)(d & (kSub - 1)) * 4u;
             out[ww] = __float_as_uint(wt);
-            atomicOr(&banks[grp], 1u << (d & 31));
         }
         __syncwarp();
-        // ---- pads: group `grp` holds ranks grp, grp + groups, ... -> its first cnt lanes; every other lane adds +0.0f
-        // to ONE dummy word behind the tile (same address in all pad lanes: a broadcast), picked in a bank none of the
-        // group's postings uses, so the padding never costs a shared-memory wavefront
+        // ---- pads: every unused slot adds +0.0f to a dummy word behind the tile.  Clean group g: lane = bank, unused
+        // where the bank has no g-th posting -- its dummy word sits in that very bank.  Dirty group x holds the ranks
+        // x, x + D, ... in its first lanes; the other lanes share ONE dummy word (same address: a broadcast) in a bank
+        // none of the group's postings uses.  Padding never costs a wavefront.
         for (int grp = 0; grp < groups; ++grp) {
-            const int cnt = (n - grp + groups - 1) / groups;
-            if (lane >= cnt) {
-                const unsigned used = banks[grp];
-                const int free_bank = __ffs(~used) - 1;  // cnt < 32 postings: a bank is free
-                int ow, ww;
-                slot_words(grp, lane, ow, ww);
-                out[ow] = (uint32_t)(kSub + free_bank) * 4u;
-                out[ww] = 0u;
+            int ow, ww;
+            slot_words(grp, lane, ow, ww);
+            if (grp < C) {
+                if (c <= grp) {
+                    out[ow] = (uint32_t)(kSub + lane) * 4u;
+                    out[ww] = 0u;
+                }
+            } else {
+                const int x = grp - C;
+                const int cnt = R > x ? (R - x + D - 1) / D : 0;
+                if (lane >= cnt) {
+                    const int free_bank = __ffs(~banks[grp]) - 1;  // cnt < 32 postings: a bank is free
+                    out[ow] = (uint32_t)(kSub + free_bank) * 4u;
+                    out[ww] = 0u;
+                }
             }
         }
         __syncwarp();

@@ -8,7 +8,7 @@
 // with >= 8 postings per sub-tile, so for those terms the index keeps, next to the CSR, every
 // (term, sub-tile) segment re-laid-out as a sequence of mask-free STEPS:
 //
-//   wide step   1 KB : [32 lanes x 4 tile byte-offsets u32][32 lanes x 4 weights f32]
+//   wide step   768 B: [32 lanes x 4 tile byte-offsets u16][32 lanes x 4 weights f32]  (a tile is 8 KB + pads: 16 bits)
 //   narrow step 256 B: 32 lanes x (tile byte-offset u32, weight f32) pairs, interleaved
 //
 //   * offsets are pre-scaled byte offsets into the warp's tile (no masking / shifting per slot);
@@ -36,11 +36,13 @@ using prw::kSubShift;
 #define PR_HOT_MIN_SEG 8
 #endif
 constexpr int kHotMinSeg = PR_HOT_MIN_SEG;  // a term is hot when it averages >= this many postings per sub-tile
-constexpr int kUnitBytes = 256;  // narrow step; a wide step is 4 units
+constexpr int kUnitBytes = 256;  // narrow step; a wide step is kWideUnits units
+constexpr int kWideUnits = 3;    // 256 B of 16-bit offsets + 512 B of weights
 #ifndef PR_HOT_WIDE_REM
 #define PR_HOT_WIDE_REM 32
 #endif
 constexpr int kWideRem = PR_HOT_WIDE_REM;  // a remainder above this many postings takes one more (padded) wide step
+static_assert(kWideRem <= 64, "a segment's unit count must split uniquely into wide steps (3 units) and at most 2 narrow ones");
 
 // 256-byte units a segment of n postings occupies: full wide steps, then the rest as narrow
 // steps (or one more wide step when the rest is > kWideRem)
@@ -51,7 +53,7 @@ __host__ __device__ __forceinline__ int seg_units(int n)
         ++w;
         r = 0;
     }
-    return 4 * w + ((r + 31) >> 5);
+    return kWideUnits * w + ((r + 31) >> 5);
 }
 
 // hot_of_row[r] = exclusive rank of row r among the rows with df >= min_df, or -1; one warp.
@@ -173,16 +175,20 @@ static __global__ void __launch_bounds__(256) hot_fill_kernel(const int64_t *ind
         const int sb = (int)r[0], n = (int)(r[1] - r[0]);
         if (n == 0) continue;
         const int units = seg_units(n);
-        const int n_wide = units >> 2, n_narrow = units & 3, groups = 4 * n_wide + n_narrow;
+        const int n_wide = units / kWideUnits, n_narrow = units % kWideUnits, groups = 4 * n_wide + n_narrow;
         uint32_t *out = reinterpret_cast<uint32_t *>(stream + (size_t)hot_off[(size_t)h * ((size_t)n_sub + 1) + g] * kUnitBytes);
-        // word index of slot (group, lane): wide steps hold [32 x uint4 offsets][32 x float4 weights], narrow steps 32 (offset, weight) pairs
-        auto slot_words = [&](int grp, int ln, int &ow, int &ww) {
+        uint16_t *out16 = reinterpret_cast<uint16_t *>(out);
+        // slot (group, lane) <- (tile byte offset, weight bits): wide steps hold [32 x 4 u16 offsets][32 x float4 weights],
+        // narrow steps 32 (u32 offset, weight) pairs
+        auto put = [&](int grp, int ln, uint32_t off, uint32_t wbits) {
             if (grp < 4 * n_wide) {
-                ow = (grp >> 2) * 256 + ln * 4 + (grp & 3);
-                ww = ow + 128;
+                const int base = (grp >> 2) * (kWideUnits * 64);  // words in front of this wide step
+                out16[2 * base + ln * 4 + (grp & 3)] = (uint16_t)off;
+                out[base + 64 + ln * 4 + (grp & 3)] = wbits;
             } else {
-                ow = n_wide * 256 + (grp - 4 * n_wide) * 64 + 2 * ln;
-                ww = ow + 1;
+                const int ow = n_wide * (kWideUnits * 64) + (grp - 4 * n_wide) * 64 + 2 * ln;
+                out[ow] = off;
+                out[ow + 1] = wbits;
             }
         };
         // ---- bank histogram (bank = tile word index mod 32 = doc % 32)
@@ -235,10 +241,7 @@ static __global__ void __launch_bounds__(256) hot_fill_kernel(const int64_t *ind
                 ln = j / D;
                 atomicOr(&banks[grp], 1u << b);
             }
-            int ow, ww;
-            slot_words(grp, ln, ow, ww);
-            out[ow] = (uint32_t)(d & (kSub - 1)) * 4u;
-            out[ww] = __float_as_uint(wt);
+            put(grp, ln, (uint32_t)(d & (kSub - 1)) * 4u, __float_as_uint(wt));
         }
         __syncwarp();
         // ---- pads: every unused slot adds +0.0f to a dummy word behind the tile.  Clean group g: lane = bank, unused
@@ -246,20 +249,14 @@ static __global__ void __launch_bounds__(256) hot_fill_kernel(const int64_t *ind
         // x, x + D, ... in its first lanes; the other lanes share ONE dummy word (same address: a broadcast) in a bank
         // none of the group's postings uses.  Padding never costs a wavefront.
         for (int grp = 0; grp < groups; ++grp) {
-            int ow, ww;
-            slot_words(grp, lane, ow, ww);
             if (grp < C) {
-                if (c <= grp) {
-                    out[ow] = (uint32_t)(kSub + lane) * 4u;
-                    out[ww] = 0u;
-                }
+                if (c <= grp) put(grp, lane, (uint32_t)(kSub + lane) * 4u, 0u);
             } else {
                 const int x = grp - C;
                 const int cnt = R > x ? (R - x + D - 1) / D : 0;
                 if (lane >= cnt) {
                     const int free_bank = __ffs(~banks[grp]) - 1;  // cnt < 32 postings: a bank is free
-                    out[ow] = (uint32_t)(kSub + free_bank) * 4u;
-                    out[ww] = 0u;
+                    put(grp, lane, (uint32_t)(kSub + free_bank) * 4u, 0u);
                 }
             }
         }

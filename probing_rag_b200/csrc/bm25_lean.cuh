@@ -8,7 +8,8 @@
 //   * ONE posting address space.  Next to the hot stream (bm25_hot.cuh) the index keeps a COLD stream: every CSR
 //     posting as an interleaved (pre-scaled tile byte offset, weight) pair, 8 bytes, at granule index = posting index;
 //     hot narrow units are interleaved pairs too.  A descriptor is (granule index u32, flags): address = base + 8 *
-//     (granule + lane [* 2]).  Two step shapes: WIDE (4 slots per lane, two 128-bit loads) and NARROW (one 64-bit load
+//     (granule + lane [* 2]).  Two step shapes: WIDE (4 slots per lane: a 64-bit load of four 16-bit offsets and a
+//     128-bit load of four weights) and NARROW (one 64-bit load
 //     for the lanes below `cnt`; the others add +0.0f to a dummy word).  No-op and END steps are narrow steps with
 //     cnt = 0, so there is no third kind, and every per-step branch tests one flag bit of a word all lanes hold.
 //   * One 128-entry descriptor ring per warp; each produced list ends with a flagged descriptor (no loop counter) and
@@ -106,10 +107,11 @@ constexpr int kCntShift = 0, kSubIdxShift = 8;
 __host__ __device__ inline size_t lean_smem_bytes(int nw) { return (size_t)nw * (kTileWords * 4 + kRing * 8) + 1024; }
 
 struct StepBuf {
-    uint4 d;   // wide: four tile byte offsets; narrow: (.x, .y) = (tile byte offset, weight bits)
+    uint2 d;   // wide: four 16-bit tile byte offsets; narrow: (.x, .y) = (tile byte offset, weight bits)
     float4 w;  // wide: four weights
     uint32_t meta;
 };
+static_assert((prw::kSub + 64) * 4 < 65536, "tile byte offsets of the hot stream are 16 bits wide");
 
 __device__ __forceinline__ uint2 ldg_stream_u2(const void *p)
 {
@@ -356,7 +358,8 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
 #pragma unroll 1
                 for (int k = k0; k < k1; ++k, ++pos) {
                     const bool wide = k < n_wide;
-                    const uint32_t unit = wide ? seg_x + 4u * (uint32_t)k : seg_x + 3u * (uint32_t)n_wide + (uint32_t)k;
+                    const uint32_t unit = wide ? seg_x + (uint32_t)prh::kWideUnits * (uint32_t)k
+                                               : seg_x + (uint32_t)(prh::kWideUnits - 1) * (uint32_t)n_wide + (uint32_t)k;
                     sts_u2(slot(pos), hot_base_g + unit * 32u, wide ? (uint32_t)kFlagWide : (32u << kCntShift));
                 }
             } else {
@@ -457,8 +460,8 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                 // ---- steps of this (sub-tile, pass), laid out in term order
                 int n_wide = 0, n = 0;
                 if (t_class == 2) {
-                    n_wide = seg_len >> 2;
-                    n = n_wide + (seg_len & 3);
+                    n_wide = seg_len / prh::kWideUnits;
+                    n = n_wide + seg_len % prh::kWideUnits;
                 } else if (t_class >= 0) {
                     n = (seg_len + 31) >> 5;
                 }
@@ -566,8 +569,8 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
                 int n_wide = 0, n = 0;
                 if (it_w0 == 0 || s == 0) {  // a chunked sub-tile continues with slot 0 only
                     if (t_class == 2) {
-                        n_wide = seg_len >> 2;
-                        n = n_wide + (seg_len & 3);
+                        n_wide = seg_len / prh::kWideUnits;
+                        n = n_wide + seg_len % prh::kWideUnits;
                     } else if (t_class >= 0) {
                         n = (seg_len + 31) >> 5;
                     }
@@ -670,17 +673,19 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
         auto issue = [&](const uint2 ds, StepBuf &b) {
             b.meta = ds.y;
             if ((int32_t)ds.y < 0) {  // wide flag; the same word in every lane: a uniform branch, cheaper than a vote + guard
-                const unsigned char *p = wide_base + ((size_t)ds.x << 3);
+                // 256 B of 16-bit offsets (8 bytes per lane), then 512 B of weights (16 bytes per lane)
+                const size_t off = (size_t)ds.x << 3;
 #if PR_LEAN_L2HINT
-                b.d = ldg_hint_u4(p, l2_keep);
-                b.w = ldg_hint_f4(p + 512, l2_keep);
+                asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;"
+                             : "=r"(b.d.x), "=r"(b.d.y) : "l"(narrow_base + off), "l"(l2_keep));
+                b.w = ldg_hint_f4(wide_base + off + 256, l2_keep);
 #else
-                b.d = ldg_stream_u4(p);
-                b.w = ldg_stream_f4(p + 512);
+                b.d = ldg_stream_u2(narrow_base + off);
+                b.w = ldg_stream_f4(wide_base + off + 256);
 #endif
             } else {
-                // lanes at or past `cnt` keep (dummy word, +0.0f).  ONE 64-bit load into (d.x, d.y) -- the first half of
-                // the offset quad, an aligned register pair -- so a narrow step's weight travels in d.y.  (Loading the
+                // lanes at or past `cnt` keep (dummy word, +0.0f).  ONE 64-bit load into (d.x, d.y) -- an aligned register
+                // pair -- so a narrow step's weight travels in d.y.  (Loading the
                 // pair into (d.x, w.x) made ptxas copy the words right behind the load: a full L2 latency stall per
                 // step; two 32-bit loads avoid that too but cost two extra L1TEX wavefronts per step.)
                 uint2 v = make_uint2(dummy_off, 0u);
@@ -722,7 +727,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 2 * PR_LEAN_CTAS : NW <= 8
         auto rmw = [&](const StepBuf &b, auto ep_c) {
             constexpr bool NEG = decltype(ep_c)::value == 1 || decltype(ep_c)::value == 2;   // sums are negative
             if ((int32_t)b.meta < 0) {
-                const uint32_t oo[4] = {b.d.x, b.d.y, b.d.z, b.d.w};
+                const uint32_t oo[4] = {b.d.x & 0xffffu, b.d.x >> 16, b.d.y & 0xffffu, b.d.y >> 16};
                 const float ww[4] = {b.w.x, b.w.y, b.w.z, b.w.w};
                 float v[4];
 #pragma unroll

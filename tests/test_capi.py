@@ -34,6 +34,7 @@ def test_version_and_argument_errors_without_gpu():
     assert L.pr_bm25_workspace_bytes(None, 4, 10) == 0
     assert L.pr_bm25_num_launches(None, 4, 10, -1) == -1 and L.pr_bm25_theta_offset(None, 4, 10) == 0
     assert L.pr_bm25_running_scores_offset(None, 4, 10) == 0
+    assert L.pr_bm25_raise_union_bound(None, 4, 10, None, 2, None, 0, None) == _lib.PR_EINVAL
     h = ctypes.c_void_p()
     assert L.pr_index_create(ctypes.byref(h), 0, 10, 0, 10, 4, 0, None, None, None) == _lib.PR_EINVAL
 
